@@ -1,0 +1,160 @@
+"""Synthetic triangulations (no Triangle / meshpy needed).
+
+The reference builds its meshes with meshpy.triangle (tests/flow_over_cyl.ipynb c3-c9,
+tests/porous_flow.ipynb), which is absent here; BASELINE.json asks for "synthetically
+triangulated meshes, generated without Triangle".  Every generator returns a ``RawMesh``
+with the four arrays ``Mesher.import_meshpy`` consumes (/root/reference/src/mesher.py:48-61):
+``points (P,2) f64``, ``elements (N,3) i32``, ``faces (F,2) i32`` (unique edges) and
+``point_markers (P,) i32``.
+
+Periodic meshes additionally carry ``point_alias`` (canonical id of every point); geometry is
+always taken from a cell's own (unwrapped) vertices, connectivity from canonical ids.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+# box markers, counter-clockwise starting at the bottom like meshpy's make_box facets
+BOTTOM, RIGHT, TOP, LEFT, OBSTACLE = 1, 2, 3, 4, 5
+
+
+@dataclass
+class RawMesh:
+    points: np.ndarray
+    elements: np.ndarray
+    faces: np.ndarray
+    point_markers: np.ndarray
+    point_alias: Optional[np.ndarray] = None   # periodic identification (canonical point id)
+    shape: Optional[tuple] = None              # (nx, ny) of the generating quad grid, if any
+
+    @property
+    def num_cells(self):
+        return self.elements.shape[0]
+
+
+def unique_edges(elements: np.ndarray, num_points: int, alias: Optional[np.ndarray] = None) -> np.ndarray:
+    """Unique undirected edges of a triangulation, one row per face, sorted by (min,max) key.
+
+    With ``alias`` the key is built from canonical point ids (periodic identification) while the
+    returned rows keep the point ids of the first half-edge that produced the key.
+    """
+    k = elements.shape[1]
+    a = elements.reshape(-1)
+    b = np.roll(elements, -1, axis=1).reshape(-1)
+    ca, cb = (a, b) if alias is None else (alias[a], alias[b])
+    key = np.minimum(ca, cb).astype(np.int64) * np.int64(num_points) + np.maximum(ca, cb).astype(np.int64)
+    _, first = np.unique(key, return_index=True)
+    del k
+    return np.stack([a[first], b[first]], axis=1).astype(np.int32)
+
+
+def triangulated_square(nx: int, ny: int, jitter: float = 0.2, seed: int = 0,
+                        periodic_x: bool = False, lx: float | None = None, ly: float | None = None) -> RawMesh:
+    """``nx x ny`` unit quads, interior vertices jittered by U(-jitter, jitter)^2, each quad split
+    along alternating diagonals ((i+j)%2), triangles counter-clockwise.
+
+    Cell numbering is row-major over quads, two triangles per quad (cell 2*(j*nx+i)+{0,1}).
+    """
+    lx = float(nx) if lx is None else lx
+    ly = float(ny) if ly is None else ly
+    xs = np.arange(nx + 1, dtype=np.float64)
+    ys = np.arange(ny + 1, dtype=np.float64)
+    X, Y = np.meshgrid(xs, ys)                      # (ny+1, nx+1), row = y
+    if jitter > 0 and nx > 1 and ny > 1:
+        rng = np.random.default_rng(seed)
+        d = rng.uniform(-jitter, jitter, size=(ny - 1, nx - 1, 2))
+        X[1:-1, 1:-1] += d[..., 0]
+        Y[1:-1, 1:-1] += d[..., 1]
+    points = np.stack([X.reshape(-1) * (lx / nx), Y.reshape(-1) * (ly / ny)], axis=1)
+
+    def pid(i, j):
+        return (j * (nx + 1) + i).astype(np.int32)
+
+    I, J = np.meshgrid(np.arange(nx), np.arange(ny))
+    I = I.reshape(-1)
+    J = J.reshape(-1)
+    p00, p10, p11, p01 = pid(I, J), pid(I + 1, J), pid(I + 1, J + 1), pid(I, J + 1)
+    even = ((I + J) % 2) == 0
+    # even quads: diagonal p00-p11 ; odd quads: diagonal p10-p01 ; both CCW
+    t0 = np.where(even[:, None], np.stack([p00, p10, p11], 1), np.stack([p00, p10, p01], 1))
+    t1 = np.where(even[:, None], np.stack([p00, p11, p01], 1), np.stack([p10, p11, p01], 1))
+    elements = np.empty((2 * nx * ny, 3), dtype=np.int32)
+    elements[0::2] = t0
+    elements[1::2] = t1
+
+    markers = np.zeros((ny + 1, nx + 1), dtype=np.int32)
+    if not periodic_x:
+        markers[:, 0] = LEFT
+        markers[:, -1] = RIGHT
+    markers[0, :] = BOTTOM
+    markers[-1, :] = TOP
+    alias = None
+    if periodic_x:
+        ids = np.arange((nx + 1) * (ny + 1), dtype=np.int32).reshape(ny + 1, nx + 1)
+        ids[:, -1] = ids[:, 0]
+        alias = ids.reshape(-1)
+    faces = unique_edges(elements, points.shape[0], alias)
+    return RawMesh(points, elements, faces, markers.reshape(-1), alias, (nx, ny))
+
+
+def masked_domain(nx: int, ny: int, lx: float, ly: float, inside_obstacle, jitter: float = 0.15,
+                  seed: int = 0) -> RawMesh:
+    """Triangulated ``lx x ly`` box with the cells whose centroid satisfies
+    ``inside_obstacle(x, y)`` removed; nodes on the obstacle outline get marker 5 (the cylinder /
+    porous-obstacle marker of tests/flow_over_cyl.ipynb c5 and tests/porous_flow.ipynb).
+    Unreferenced points are dropped and ids compacted.
+    """
+    m = triangulated_square(nx, ny, jitter=jitter, seed=seed, lx=lx, ly=ly)
+    cen = m.points[m.elements].mean(axis=1)
+    keep = ~np.asarray(inside_obstacle(cen[:, 0], cen[:, 1]), dtype=bool)
+    el = m.elements[keep]
+    used = np.zeros(m.points.shape[0], dtype=bool)
+    used[el.reshape(-1)] = True
+    remap = -np.ones(m.points.shape[0], dtype=np.int32)
+    remap[used] = np.arange(int(used.sum()), dtype=np.int32)
+    el = remap[el]
+    pts = m.points[used]
+    mk = m.point_markers[used].copy()
+    faces = unique_edges(el, pts.shape[0])
+    # boundary edges = edges with exactly one adjacent cell; their unmarked nodes are obstacle nodes
+    a = el.reshape(-1)
+    b = np.roll(el, -1, axis=1).reshape(-1)
+    key = np.minimum(a, b).astype(np.int64) * pts.shape[0] + np.maximum(a, b)
+    uk, cnt = np.unique(key, return_counts=True)
+    bkeys = uk[cnt == 1]
+    bn = np.unique(np.concatenate([bkeys // pts.shape[0], bkeys % pts.shape[0]]))
+    obst = bn[mk[bn] == 0]
+    mk[obst] = OBSTACLE
+    return RawMesh(pts, el.astype(np.int32), faces, mk, None, None)
+
+
+def cylinder_channel(scale: int = 1, seed: int = 0) -> RawMesh:
+    """Flow-over-cylinder domain of tests/flow_over_cyl.ipynb c4-c7: box (0,0)-(60,20), circle r=1
+    at (10,10).  ``scale=1`` -> 60x20 quads (2.4k cells); ``scale=9`` ~ 194k cells (config 2)."""
+    nx, ny = 60 * scale, 20 * scale
+    return masked_domain(nx, ny, 60.0, 20.0, lambda x, y: (x - 10.0) ** 2 + (y - 10.0) ** 2 < 1.0,
+                         seed=seed)
+
+
+def porous_channel(scale: int = 1, seed: int = 0, n_obst: int = 60) -> RawMesh:
+    """Porous-flow-like domain (tests/porous_flow.ipynb geometry: box (-93,0)-(279,186) with 60
+    obstacles); obstacles here are deterministic pseudo-random discs since the outline blob
+    (tests/test_bmp.mat) need not travel.  ``scale=4`` ~ 2M cells (config 3)."""
+    lx, ly = 372.0, 186.0
+    nx, ny = 186 * scale, 93 * scale
+    rng = np.random.default_rng(1234 + seed)
+    cx = rng.uniform(0.12 * lx, 0.88 * lx, n_obst)
+    cy = rng.uniform(0.08 * ly, 0.92 * ly, n_obst)
+    r = rng.uniform(4.0, 9.0, n_obst)
+
+    def inside(x, y):
+        out = np.zeros(x.shape, dtype=bool)
+        for i in range(n_obst):
+            out |= (x - cx[i]) ** 2 + (y - cy[i]) ** 2 < r[i] ** 2
+        return out
+    m = masked_domain(nx, ny, lx, ly, inside, seed=seed)
+    m.points[:, 0] -= 93.0
+    return m
