@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- MCUPS (D2Q9 cell-updates/s) of the FVDBM time-step hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (CUDA)
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: oracle C/OpenMP port
+
+Workload (BASELINE.json configs[3]): synthetic triangulated square, nx=ny=2236 quads
+-> 9 999 392 triangles, jitter 0.2 (seed 0), alternating diagonals, x-periodic, y walls (bottom
+vel 0, top lid vel (0.1,0)), D2Q9(tau=0.8, dt=0.1), Lax-Wendroff, fp32, perturbed equilibrium
+start.  One bench "step" = one `Environment.step(inner)` call = `inner` FVDBM iterations of the
+whole mesh (default 100).  `value` = cells * inner * K / device time (CUDA events on the engine's
+stream, inputs resident in HBM).  `e2e` = same call through the public API with pinned HOST
+buffers: populations uploaded and rho/vel downloaded inside the timed region, every step.
+Inputs exceed L2 (1.3 GB touched per iteration vs 126 MB), so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = {("f32", "lax_wendroff"): (108, 28), ("f32", "upwind"): (108, 20),
+         ("f64", "lax_wendroff"): (192, 48), ("f64", "upwind"): (192, 36)}
+
+
+def build_problem(nx, ny, scheme, seed=0, periodic=True):
+    import fvdbm_jax_b200 as fb
+    from fvdbm_jax_b200 import meshgen
+    t0 = time.time()
+    raw = meshgen.triangulated_square(nx, ny, jitter=0.2, seed=seed, periodic_x=periodic)
+    m = fb.Mesher()
+    m.import_meshpy(raw)
+    m.calc_mesh_properties()
+    dyn = fb.D2Q9(tau=0.8, delta_t=0.1)
+    cells, faces, nodes = m.to_env(dyn, flux_method=scheme)
+    nodes = m.set_vel_node(nodes, meshgen.BOTTOM, np.array([0.0, 0.0]))
+    nodes = m.set_vel_node(nodes, meshgen.TOP, np.array([0.1, 0.0]))
+    if not periodic:
+        nodes = m.set_vel_node(nodes, meshgen.LEFT, np.array([0.0, 0.0]))
+        nodes = m.set_vel_node(nodes, meshgen.RIGHT, np.array([0.0, 0.0]))
+    c = m.cell_centers
+    rho = 1 + 0.01 * np.sin(2 * np.pi * c[:, 0] / nx) * np.sin(2 * np.pi * c[:, 1] / ny)
+    u = 0.05 * np.stack([np.sin(2 * np.pi * c[:, 1] / ny), np.sin(2 * np.pi * c[:, 0] / nx)], axis=1)
+    cells.pdf = dyn.calc_eq(rho, u).astype(np.float32)
+    return m, dyn, cells, faces, nodes, time.time() - t0
+
+
+def static_state(cells, faces, nodes):
+    static = {"cells.face_indices": cells.face_indices, "cells.face_normals": cells.face_normals,
+              "faces.nodes_index": faces.nodes_index, "faces.stencil_cells_index": faces.stencil_cells_index,
+              "faces.stencil_dists": faces.stencil_dists, "faces.n": faces.n, "faces.L": faces.L,
+              "nodes.type": nodes.type, "nodes.cells_index": nodes.cells_index, "nodes.cell_dists": nodes.cell_dists}
+    state = {"cells.pdf": cells.pdf, "nodes.pdf": nodes.pdf, "nodes.rho": nodes.rho, "nodes.vel": nodes.vel}
+    return static, state
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out, _ = self.proc.communicate(timeout=10)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(scheme, seconds=12.0, nx=1000):
+    """Oracle C/OpenMP port on the host cores over a bounded sample of the same mesh family."""
+    from oracle.step_c import COracle, threads
+    m, dyn, cells, faces, nodes, _ = build_problem(nx, nx, scheme)
+    static, state = static_state(cells, faces, nodes)
+    o = COracle(static, state, 9, dyn.tau, dyn.delta_t, scheme, np.float32)
+    n = cells.face_indices.shape[0]
+    o.step(3)
+    t0 = time.perf_counter(); o.step(5); per = (time.perf_counter() - t0) / 5
+    iters = max(5, int(seconds / per))
+    t0 = time.perf_counter(); o.step(iters); dt = time.perf_counter() - t0
+    return {"value": n * iters / dt / 1e6, "unit": "MCUPS", "cores": threads(), "kind": "port",
+            "sample": f"{n} cells (nx=ny={nx}, same mesh family) x {iters} iterations, oracle/step_c.c OpenMP fp32; "
+                      "JAX is not installed on the box so the reference's jitted CPU step cannot be timed"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; JAX absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.step_c import COracle, threads
+    nx = args.ref_nx
+    m, dyn, cells, faces, nodes, _ = build_problem(nx, nx, args.scheme)
+    static, state = static_state(cells, faces, nodes)
+    o = COracle(static, state, 9, dyn.tau, dyn.delta_t, args.scheme, np.float32)
+    n = cells.face_indices.shape[0]
+    inner = args.ref_inner
+    for _ in range(args.warmup):
+        o.step(inner)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.step(inner)
+    dt = time.perf_counter() - t0
+    val = n * inner * args.steps / dt / 1e6
+    sample = f"{n} cells (nx=ny={nx}) x {inner} iterations per step, oracle/step_c.c OpenMP fp32"
+    line = {"impl": "reference", "metric": "MCUPS", "value": val, "unit": "MCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.nx, None, inner),
+            "cpu_baseline": {"value": val, "unit": "MCUPS", "cores": threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "MCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, nx, cells, inner):
+    return {"workload": f"synthetic triangulated square nx=ny={nx} ({'%d cells' % cells if cells else '2*nx*ny cells'}), "
+                        f"x-periodic + y walls (lid 0.1), D2Q9 tau=0.8 dt=0.1, {args.scheme}, per-GPU under weak scaling",
+            "inner_iterations_per_step": inner, "scheme": args.scheme, "l2": "inputs exceed L2 (no flush needed)",
+            "reorder": args.reorder, "variant": args.variant, "tile_cells": args.tile, "stages": args.stages,
+            "reverse_sweep": args.reverse, "graph_steps": args.graph}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=2236, help="quads per side (cells = 2*nx*nx per GPU)")
+    ap.add_argument("--inner", type=int, default=100, help="FVDBM iterations per bench step")
+    ap.add_argument("--scheme", default="lax_wendroff", choices=["lax_wendroff", "upwind"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--reorder", default="hilbert")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--reverse", type=int, default=-1)
+    ap.add_argument("--graph", type=int, default=-1)
+    ap.add_argument("--ctas", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-nx", type=int, default=1000)
+    ap.add_argument("--ref-inner", type=int, default=10)
+    ap.add_argument("--sweep", action="store_true", help="print one extra JSON line per kernel configuration")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import fvdbm_jax_b200 as fb
+    from fvdbm_jax_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    real = np.float32 if args.dtype == "f32" else np.float64
+
+    if world > 1:
+        from fvdbm_jax_b200.distributed import DistributedEnvironment
+        denv = DistributedEnvironment.weak_scaling_square(args.nx, args.scheme, real, rank, world, local,
+                                                          reorder=args.reorder)
+        env, n_local, n_global = denv, denv.n_owned, denv.n_global
+        stepper = denv
+    else:
+        m, dyn, cells, faces, nodes, t_mesh = build_problem(args.nx, args.nx, args.scheme)
+        env = fb.Environment(cells, faces, nodes, dtype=real, device=local, reorder=args.reorder)
+        env.init()
+        env.build()
+        n_local = n_global = cells.face_indices.shape[0]
+        stepper = env
+    for opt, val in ((_lib.OPT_VARIANT, args.variant), (_lib.OPT_TILE_CELLS, args.tile), (_lib.OPT_STAGES, args.stages)):
+        if val > 0:
+            stepper.set_option(opt, val)
+    for opt, val in ((_lib.OPT_REVERSE_SWEEP, args.reverse), (_lib.OPT_GRAPH_STEPS, args.graph), (_lib.OPT_CTAS_PER_SM, args.ctas)):
+        if val >= 0:
+            stepper.set_option(opt, val)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    inner = args.inner
+    launches0 = stepper.info(_lib.INFO_LAUNCHES)
+    for _ in range(args.warmup):
+        stepper.step(inner)
+    barrier()
+    launches1 = stepper.info(_lib.INFO_LAUNCHES)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ms = stepper.step_timed(inner * args.steps)        # CUDA events on the engine's stream, K steps
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = stepper.info(_lib.INFO_LAUNCHES) - launches1
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_global * inner * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- e2e through the public API with pinned host buffers --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_pdf = torch.empty((n_local, 9), dtype=torch.float32 if real is np.float32 else torch.float64).pin_memory()
+        rho_out = torch.empty((n_local, 1), dtype=host_pdf.dtype).pin_memory()
+        vel_out = torch.empty((n_local, 2), dtype=host_pdf.dtype).pin_memory()
+        stepper.get_into("cells.pdf", host_pdf.numpy())
+        reps = max(2, min(args.steps, 5))
+
+        def one():
+            stepper.set_cells_pdf(host_pdf.numpy())
+            stepper.step(inner)
+            stepper.get_into("cells.rho", rho_out.numpy())
+            stepper.get_into("cells.vel", vel_out.numpy())
+        one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_global * inner * reps / dt / 1e6, "unit": "MCUPS",
+               "h2d_bytes_per_step": int(host_pdf.numel() * host_pdf.element_size()),
+               "d2h_bytes_per_step": int((rho_out.numel() + vel_out.numel()) * rho_out.element_size()),
+               "note": f"Environment: cells.pdf <- pinned host; step({inner}); cells.rho, cells.vel -> pinned host; per GPU"}
+
+    if rank != 0:
+        return
+    per_cell, per_face = B_ALG[(args.dtype, args.scheme)]
+    if world == 1:
+        f_over_n = faces.n.shape[0] / n_local
+    else:
+        f_over_n = denv.faces_per_cell
+    b_alg = per_cell + per_face * f_over_n
+    peak, peak_src = measured_peak()
+    iter_ms = ms / (inner * args.steps)
+    achieved = n_local * b_alg / (iter_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_fused_tma" if stepper.info(_lib.INFO_VARIANT) == 2 else "k_fused_direct",
+                "algorithmic_bytes_per_cell_update": b_alg, "cells_per_launch": n_local, "avg_launch_ms": iter_ms,
+                "peak_source": peak_src,
+                "note": "avg_launch_ms = event time / iterations (includes the O(sqrt N) node kernel); traffic from "
+                        "profiles/ ncu capture when available"}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    line = {"metric": "MCUPS", "value": value, "unit": "MCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, args.nx, n_local, inner), "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.scheme)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,699 @@
+// api.cu -- C ABI of libfvdbm_b200.so (include/fvdbm_b200.h): handle, dispatch, transfers.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/fvdbm_b200.h"
+#include "plan.hpp"
+#include "kernels.cuh"
+
+using namespace fvdbm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Engine {
+    virtual ~Engine() {}
+    std::string err;
+    virtual int step(int n) = 0;
+    virtual int step_timed(int n, float* ms) = 0;
+    virtual int step_phase(int phase) = 0;
+    virtual int sync() = 0;
+    virtual int get(int field, void* dst, size_t bytes) = 0;
+    virtual int set(int field, const void* src, size_t bytes) = 0;
+    virtual int set_params(double tau, double dt) = 0;
+    virtual int set_option(int opt, int64_t v) = 0;
+    virtual int info(int key, int64_t* v) const = 0;
+    virtual int halo_set_lists(const int32_t* s, int64_t ns, const int32_t* r, int64_t nr) = 0;
+    virtual int halo_pack(void* buf) = 0;
+    virtual int halo_unpack(const void* buf) = 0;
+    virtual void* stream_handle() = 0;
+};
+
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            err = std::string(#expr) + ": " + cudaGetErrorString(e_);                         \
+            return FVDBM_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t upload(const T* v, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, v, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <typename real, int Q, int K, int SCHEME>
+struct EngineT final : Engine {
+    Plan<real> plan;
+    Params<real> P{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int mode = FVDBM_MODE_FUSED;
+    int variant = FVDBM_VARIANT_TMA;
+    int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
+    int num_sms = 148;
+    int cur = 0;
+    int64_t steps = 0, launches = 0;
+    bool phase0_done = false;
+
+    DevBuf<real> pdf[2];
+    DevBuf<int32_t> ccode, bf_na, bf_nb, pos, ipos, ring_off, ring_cell, tn_type;
+    DevBuf<real> ccoef, bf_ratio, ring_w, npdf, nrho, nvel;
+    DevBuf<int32_t> s_cface, s_csign, s_fcell, s_fnode;
+    DevBuf<real> s_fdist, s_fn, s_fL;
+    DevBuf<real> s_rho, s_ux, s_uy, s_feq, s_flux;     // staged dynamics (lazy)
+    DevBuf<real> scratch;                              // export/import staging
+    DevBuf<int32_t> halo_send, halo_recv;
+    std::map<int, cudaGraphExec_t> graphs;             // key: starting `cur`
+
+    ~EngineT() override {
+        cudaSetDevice(device);
+        drop_graphs();
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    }
+    void drop_graphs() {
+        for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+        graphs.clear();
+    }
+
+    void fill_params(const fvdbm_desc& d) {
+        for (int q = 0; q < 16; ++q) P.w[q] = (real)d.lat_w[q];
+        const real cs2 = (real)d.cs2, t4 = (real)d.two_cs4, t2 = (real)d.two_cs2, t6 = (real)d.two_cs6;
+        P.inv_cs2 = real(1) / cs2;
+        P.inv_2cs4 = real(1) / t4;
+        P.inv_2cs2 = real(1) / t2;
+        P.inv_2cs6 = (Q == 13) ? real(1) / t6 : real(0);
+        P.three_inv_2cs4 = real(3) / t4;
+        P.inv_tau = (real)(1.0 / d.tau);
+        P.dt = (real)d.delta_t;
+    }
+
+    int init(const fvdbm_desc& d) {
+        if (!plan.build(d)) { err = plan.error; return FVDBM_ERR_ARG; }
+        device = d.device_id;
+        int ndev = 0;
+        CU_TRY(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev) { err = "device_id out of range"; return FVDBM_ERR_ARG; }
+        CU_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, device));
+        num_sms = prop.multiProcessorCount;
+        CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        fill_params(d);
+        mode = d.mode == FVDBM_MODE_STAGED ? FVDBM_MODE_STAGED : FVDBM_MODE_FUSED;
+        if (mode == FVDBM_MODE_FUSED && !plan.fused_ok) {
+            if (d.mode == FVDBM_MODE_FUSED) { err = "fused mode unavailable: " + plan.why_not; return FVDBM_ERR_ARG; }
+            mode = FVDBM_MODE_STAGED;
+        }
+        const size_t npdf_elems = (size_t)(plan.Npad / TW) * Q * TW;
+        CU_TRY(pdf[0].alloc(npdf_elems));
+        CU_TRY(pdf[1].alloc(npdf_elems));
+        CU_TRY(cudaMemsetAsync(pdf[0].p, 0, pdf[0].bytes(), stream));
+        CU_TRY(cudaMemsetAsync(pdf[1].p, 0, pdf[1].bytes(), stream));
+        CU_TRY(pos.upload(plan.pos, stream));
+        CU_TRY(ipos.upload(plan.ipos, stream));
+        if (plan.fused_ok) {
+            CU_TRY(ccode.upload(plan.ccode, stream));
+            CU_TRY(ccoef.upload(plan.ccoef, stream));
+            CU_TRY(bf_na.upload(plan.bf_na, stream));
+            CU_TRY(bf_nb.upload(plan.bf_nb, stream));
+            CU_TRY(bf_ratio.upload(plan.bf_ratio, stream));
+        }
+        CU_TRY(ring_off.upload(plan.ring_off, stream));
+        CU_TRY(ring_cell.upload(plan.ring_cell, stream));
+        CU_TRY(ring_w.upload(plan.ring_w, stream));
+        CU_TRY(tn_type.upload(plan.tn_type, stream));
+        CU_TRY(npdf.upload(plan.tn_pdf, stream));
+        CU_TRY(nrho.upload(plan.tn_rho, stream));
+        CU_TRY(nvel.upload(plan.tn_vel, stream));
+        CU_TRY(s_cface.upload(plan.s_cface, stream));
+        CU_TRY(s_csign.upload(plan.s_csign, stream));
+        CU_TRY(s_fcell.upload(plan.s_fcell, stream));
+        CU_TRY(s_fnode.upload(plan.s_fnode, stream));
+        CU_TRY(s_fdist.upload(static_cast<const real*>(d.face_dists), (size_t)plan.F * 2, stream));
+        CU_TRY(s_fn.upload(static_cast<const real*>(d.face_n), (size_t)plan.F * 2, stream));
+        CU_TRY(s_fL.upload(static_cast<const real*>(d.face_L), (size_t)plan.F, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        // host staging vectors are no longer needed
+        plan.ccode = {}; plan.ccoef = {}; plan.s_cface = {}; plan.s_csign = {}; plan.s_fcell = {}; plan.s_fnode = {};
+        plan.ring_cell = {}; plan.ring_w = {}; plan.tn_pdf = {};
+        int rc = set(FVDBM_CELL_PDF, d.cell_pdf, (size_t)plan.N * Q * sizeof(real));
+        if (rc) return rc;
+        // opt-in shared memory for the TMA kernel
+        CU_TRY(cudaFuncSetAttribute(k_fused_tma<real, Q, K, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)prop.sharedMemPerBlockOptin));
+        max_smem = prop.sharedMemPerBlockOptin;
+        if (const char* e = getenv("FVDBM_VARIANT")) variant = atoi(e);
+        if (const char* e = getenv("FVDBM_TILE_CELLS")) tile_cells = atoi(e);
+        if (const char* e = getenv("FVDBM_STAGES")) stages = atoi(e);
+        if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
+        if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
+        if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
+        if (variant == FVDBM_VARIANT_AUTO) variant = FVDBM_VARIANT_TMA;
+        return sanitize_options();
+    }
+    size_t max_smem = 0;
+    int occ_cache = 0;
+
+    int sanitize_options() {
+        if (variant != FVDBM_VARIANT_DIRECT && variant != FVDBM_VARIANT_TMA) { err = "unknown variant"; return FVDBM_ERR_ARG; }
+        if (tile_cells != 128 && tile_cells != 256 && tile_cells != 512) { err = "tile_cells must be 128, 256 or 512"; return FVDBM_ERR_ARG; }
+        if (stages < 2 || stages > 8) { err = "stages must be in 2..8"; return FVDBM_ERR_ARG; }
+        while (stages > 2 && kTmaHeader + stages * tma_stage_bytes<real, Q, K, SCHEME>(tile_cells) > max_smem) --stages;
+        while (tile_cells > 128 && kTmaHeader + stages * tma_stage_bytes<real, Q, K, SCHEME>(tile_cells) > max_smem) tile_cells /= 2;
+        if (graph_steps < 0) graph_steps = 0;
+        if (graph_steps & 1) ++graph_steps;
+        return FVDBM_OK;
+    }
+
+    // ---------------------------------------------------------------- launches
+    FusedArgs<real> fused_args(int64_t begin, int64_t end) const {
+        FusedArgs<real> a;
+        a.P = P;
+        a.pdf_in = pdf[cur].p; a.pdf_out = pdf[cur ^ 1].p;
+        a.ccode = ccode.p; a.ccoef = ccoef.p;
+        a.G.bf_na = bf_na.p; a.G.bf_nb = bf_nb.p; a.G.bf_ratio = bf_ratio.p;
+        a.G.npdf = npdf.p; a.G.NTpad = plan.NTpad;
+        a.cell_begin = begin; a.cell_end = end;
+        a.reverse = (reverse_sweep && cur == 1) ? 1 : 0;
+        return a;
+    }
+
+    int launch_nodes() {
+        if (plan.NA == 0) return FVDBM_OK;
+        NodeArgs<real> a;
+        a.P = P; a.pdf = pdf[cur].p;
+        a.ring_off = ring_off.p; a.ring_cell = ring_cell.p; a.ring_w = ring_w.p; a.tn_type = tn_type.p;
+        a.npdf = npdf.p; a.nrho = nrho.p; a.nvel = nvel.p; a.NTpad = plan.NTpad; a.NA = (int)plan.NA;
+        k_nodes<real, Q><<<blocks_for(plan.NA * 32, 256), 256, 0, stream>>>(a);
+        ++launches;
+        CU_TRY(cudaGetLastError());
+        return FVDBM_OK;
+    }
+
+    int launch_fused(int64_t begin, int64_t end) {
+        if (end <= begin) return FVDBM_OK;
+        FusedArgs<real> a = fused_args(begin, end);
+        if (variant == FVDBM_VARIANT_DIRECT) {
+            k_fused_direct<real, Q, K, SCHEME><<<blocks_for(end - begin, 256), 256, 0, stream>>>(a);
+        } else {
+            const size_t smem = kTmaHeader + (size_t)stages * tma_stage_bytes<real, Q, K, SCHEME>(tile_cells);
+            int per_sm = ctas_per_sm;
+            if (per_sm <= 0) {
+                if (occ_cache <= 0) {
+                    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_fused_tma<real, Q, K, SCHEME>, tile_cells, smem));
+                    if (occ_cache < 1) occ_cache = 1;
+                }
+                per_sm = occ_cache;
+            }
+            const int64_t ntiles = (end - begin) / tile_cells;
+            int64_t grid = (int64_t)num_sms * per_sm;
+            if (grid > ntiles) grid = ntiles;
+            k_fused_tma<real, Q, K, SCHEME><<<(unsigned)grid, tile_cells, smem, stream>>>(a, stages);
+        }
+        ++launches;
+        CU_TRY(cudaGetLastError());
+        return FVDBM_OK;
+    }
+
+    int ensure_staged_buffers() {
+        if (s_flux.p) return FVDBM_OK;
+        CU_TRY(s_flux.alloc((size_t)plan.F * Q));
+        if (mode == FVDBM_MODE_STAGED) {
+            CU_TRY(s_rho.alloc(plan.Npad)); CU_TRY(s_ux.alloc(plan.Npad)); CU_TRY(s_uy.alloc(plan.Npad));
+            CU_TRY(s_feq.alloc(pdf[0].n));
+        }
+        return FVDBM_OK;
+    }
+
+    int launch_faces(const real* src_pdf) {
+        FaceArgs<real> a;
+        a.P = P; a.pdf = src_pdf; a.fcell = s_fcell.p; a.fnode = s_fnode.p; a.fdist = s_fdist.p; a.fn = s_fn.p;
+        a.fL = s_fL.p; a.npdf = npdf.p; a.NTpad = plan.NTpad; a.F = plan.F;
+        a.last_pos = plan.pos[plan.N - 1]; a.flux = s_flux.p;
+        k_s_faces<real, Q, SCHEME><<<blocks_for(plan.F, 256), 256, 0, stream>>>(a);
+        ++launches;
+        CU_TRY(cudaGetLastError());
+        return FVDBM_OK;
+    }
+
+    int step_staged_once() {
+        int rc = ensure_staged_buffers();
+        if (rc) return rc;
+        k_s_moments<real, Q><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, pdf[cur].p, ipos.p, plan.Npad, s_rho.p,
+                                                                             s_ux.p, s_uy.p, s_feq.p);
+        ++launches;
+        if ((rc = launch_nodes())) return rc;
+        if ((rc = launch_faces(pdf[cur].p))) return rc;
+        k_s_cells<real, Q, K><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, pdf[cur].p, s_feq.p, s_flux.p, s_cface.p,
+                                                                            s_csign.p, ipos.p, plan.Npad, plan.No, pdf[cur ^ 1].p);
+        ++launches;
+        CU_TRY(cudaGetLastError());
+        if (plan.No < plan.N) {   // halo copies are refreshed by the caller; keep them readable in both buffers
+            err = "staged mode does not support halo cells"; return FVDBM_ERR_STATE;
+        }
+        cur ^= 1; ++steps;
+        return FVDBM_OK;
+    }
+
+    int64_t owned_end() const { return round_up(plan.Oend, PAD_TO); }
+
+    int step_fused_once() {
+        int rc;
+        if (!phase0_done && (rc = launch_fused(0, plan.Bstart))) return rc;
+        phase0_done = false;
+        if ((rc = launch_nodes())) return rc;
+        if ((rc = launch_fused(plan.Bstart, owned_end()))) return rc;
+        cur ^= 1; ++steps;
+        return FVDBM_OK;
+    }
+
+    int step_once() { return mode == FVDBM_MODE_STAGED ? step_staged_once() : step_fused_once(); }
+
+    int step_phase(int phase) override {
+        CU_TRY(cudaSetDevice(device));
+        if (mode != FVDBM_MODE_FUSED) { err = "step_phase needs the fused mode"; return FVDBM_ERR_STATE; }
+        if (phase == 0) {
+            if (phase0_done) { err = "phase 0 already issued"; return FVDBM_ERR_STATE; }
+            int rc = launch_fused(0, plan.Bstart);
+            if (rc) return rc;
+            phase0_done = true;
+            return FVDBM_OK;
+        }
+        if (phase == 1) return step_fused_once();
+        err = "phase must be 0 or 1";
+        return FVDBM_ERR_ARG;
+    }
+
+    int build_graph(int start_cur, cudaGraphExec_t* out) {
+        cudaGraph_t g = nullptr;
+        const int64_t s0 = steps, l0 = launches;
+        CU_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = FVDBM_OK;
+        for (int i = 0; i < graph_steps && rc == FVDBM_OK; ++i) rc = step_once();
+        cudaError_t e = cudaStreamEndCapture(stream, &g);
+        steps = s0; launches = l0; cur = start_cur;
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) { err = std::string("graph capture: ") + cudaGetErrorString(e); return FVDBM_ERR_CUDA; }
+        e = cudaGraphInstantiate(out, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { err = std::string("graph instantiate: ") + cudaGetErrorString(e); return FVDBM_ERR_CUDA; }
+        return FVDBM_OK;
+    }
+
+    int step(int n) override {
+        if (n < 0) { err = "nsteps must be >= 0"; return FVDBM_ERR_ARG; }
+        CU_TRY(cudaSetDevice(device));
+        int rc;
+        if (mode == FVDBM_MODE_STAGED && (rc = ensure_staged_buffers())) return rc;
+        while (n > 0) {
+            if (graph_steps > 0 && n >= graph_steps && !phase0_done) {
+                auto it = graphs.find(cur);
+                if (it == graphs.end()) {
+                    cudaGraphExec_t ge;
+                    const int64_t l0 = launches;
+                    // count launches of one captured batch by replaying the bookkeeping
+                    if ((rc = build_graph(cur, &ge))) return rc;
+                    (void)l0;
+                    it = graphs.emplace(cur, ge).first;
+                }
+                CU_TRY(cudaGraphLaunch(it->second, stream));
+                steps += graph_steps;
+                launches += (int64_t)graph_steps * launches_per_step();
+                n -= graph_steps;           // graph_steps is even: `cur` is unchanged
+            } else {
+                if ((rc = step_once())) return rc;
+                --n;
+            }
+        }
+        return FVDBM_OK;
+    }
+
+    int64_t launches_per_step() const {
+        if (mode == FVDBM_MODE_STAGED) return 3 + (plan.NA > 0 ? 1 : 0);
+        return (plan.NA > 0 ? 1 : 0) + (plan.Bstart > 0 ? 1 : 0) + (owned_end() > plan.Bstart ? 1 : 0);
+    }
+
+    int step_timed(int n, float* ms) override {
+        CU_TRY(cudaSetDevice(device));
+        cudaEvent_t e0, e1;
+        CU_TRY(cudaEventCreate(&e0));
+        CU_TRY(cudaEventCreate(&e1));
+        CU_TRY(cudaEventRecord(e0, stream));
+        int rc = step(n);
+        if (rc == FVDBM_OK) {
+            cudaEventRecord(e1, stream);
+            cudaError_t e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess) { err = std::string("step_timed: ") + cudaGetErrorString(e); rc = FVDBM_ERR_CUDA; }
+            else if (ms) cudaEventElapsedTime(ms, e0, e1);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return rc;
+    }
+
+    int sync() override {
+        CU_TRY(cudaSetDevice(device));
+        CU_TRY(cudaStreamSynchronize(stream));
+        CU_TRY(cudaGetLastError());
+        return FVDBM_OK;
+    }
+
+    // ---------------------------------------------------------------- transfers
+    int need_scratch(size_t elems) {
+        if (scratch.n >= elems) return FVDBM_OK;
+        CU_TRY(scratch.alloc(elems));
+        return FVDBM_OK;
+    }
+
+    int get(int field, void* dst, size_t bytes) override {
+        CU_TRY(cudaSetDevice(device));
+        if (!dst) { err = "dst is null"; return FVDBM_ERR_ARG; }
+        const int64_t N = plan.N, F = plan.F, Pn = plan.P;
+        auto expect = [&](size_t elems) {
+            if (bytes != elems * sizeof(real)) { err = "size mismatch for field"; return false; }
+            return true;
+        };
+        int rc;
+        switch (field) {
+        case FVDBM_CELL_PDF: case FVDBM_CELL_PDF_PREV: {
+            if (!expect((size_t)N * Q)) return FVDBM_ERR_ARG;
+            if (field == FVDBM_CELL_PDF_PREV && steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
+            if ((rc = need_scratch((size_t)N * Q))) return rc;
+            const real* src = pdf[field == FVDBM_CELL_PDF ? cur : cur ^ 1].p;
+            k_export_cells<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(src, pos.p, N, scratch.p);
+            ++launches;
+            break;
+        }
+        case FVDBM_CELL_RHO: case FVDBM_CELL_VEL: case FVDBM_CELL_PDF_EQ: {
+            const size_t per = field == FVDBM_CELL_RHO ? 1 : field == FVDBM_CELL_VEL ? 2 : Q;
+            if (!expect((size_t)N * per)) return FVDBM_ERR_ARG;
+            if (steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
+            if ((rc = need_scratch((size_t)N * per))) return rc;
+            k_export_moments<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(
+                P, pdf[cur ^ 1].p, pos.p, N, field == FVDBM_CELL_RHO ? scratch.p : nullptr,
+                field == FVDBM_CELL_VEL ? scratch.p : nullptr, field == FVDBM_CELL_PDF_EQ ? scratch.p : nullptr);
+            ++launches;
+            break;
+        }
+        case FVDBM_FACE_FLUX: {
+            if (!expect((size_t)F * Q)) return FVDBM_ERR_ARG;
+            if (steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
+            if ((rc = ensure_staged_buffers())) return rc;
+            if (mode != FVDBM_MODE_STAGED && (rc = launch_faces(pdf[cur ^ 1].p))) return rc;
+            CU_TRY(cudaMemcpyAsync(dst, s_flux.p, bytes, cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            return FVDBM_OK;
+        }
+        case FVDBM_NODE_PDF: case FVDBM_NODE_RHO: case FVDBM_NODE_VEL: {
+            const size_t per = field == FVDBM_NODE_RHO ? 1 : field == FVDBM_NODE_VEL ? 2 : Q;
+            if (!expect((size_t)Pn * per)) return FVDBM_ERR_ARG;
+            const DevBuf<real>& src = field == FVDBM_NODE_RHO ? nrho : field == FVDBM_NODE_VEL ? nvel : npdf;
+            std::vector<real> host(src.n);
+            if (src.n) CU_TRY(cudaMemcpyAsync(host.data(), src.p, src.bytes(), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            real* out = static_cast<real*>(dst);
+            for (int64_t t = 0; t < plan.NT; ++t)
+                for (size_t j = 0; j < per; ++j) out[(size_t)plan.tn_orig[t] * per + j] = host[j * plan.NTpad + t];
+            return FVDBM_OK;
+        }
+        default: err = "unknown field"; return FVDBM_ERR_ARG;
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(dst, scratch.p, bytes, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        return FVDBM_OK;
+    }
+
+    int set(int field, const void* src, size_t bytes) override {
+        CU_TRY(cudaSetDevice(device));
+        if (!src) { err = "src is null"; return FVDBM_ERR_ARG; }
+        const int64_t N = plan.N, Pn = plan.P;
+        int rc;
+        switch (field) {
+        case FVDBM_CELL_PDF: {
+            if (bytes != (size_t)N * Q * sizeof(real)) { err = "size mismatch for field"; return FVDBM_ERR_ARG; }
+            if ((rc = need_scratch((size_t)N * Q))) return rc;
+            CU_TRY(cudaMemcpyAsync(scratch.p, src, bytes, cudaMemcpyHostToDevice, stream));
+            k_import_cells<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(pdf[cur].p, pos.p, N, scratch.p);
+            ++launches;
+            CU_TRY(cudaGetLastError());
+            if (plan.No < plan.N) {     // halo copies must be valid in both ping-pong buffers
+                k_import_cells<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(pdf[cur ^ 1].p, pos.p, N, scratch.p);
+                ++launches;
+            }
+            CU_TRY(cudaStreamSynchronize(stream));
+            return FVDBM_OK;
+        }
+        case FVDBM_NODE_PDF: case FVDBM_NODE_RHO: case FVDBM_NODE_VEL: {
+            const size_t per = field == FVDBM_NODE_RHO ? 1 : field == FVDBM_NODE_VEL ? 2 : Q;
+            if (bytes != (size_t)Pn * per * sizeof(real)) { err = "size mismatch for field"; return FVDBM_ERR_ARG; }
+            DevBuf<real>& dstb = field == FVDBM_NODE_RHO ? nrho : field == FVDBM_NODE_VEL ? nvel : npdf;
+            std::vector<real> host(dstb.n, real(0));
+            const real* in = static_cast<const real*>(src);
+            for (int64_t t = 0; t < plan.NT; ++t)
+                for (size_t j = 0; j < per; ++j) host[j * plan.NTpad + t] = in[(size_t)plan.tn_orig[t] * per + j];
+            if (dstb.n) CU_TRY(cudaMemcpyAsync(dstb.p, host.data(), dstb.bytes(), cudaMemcpyHostToDevice, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            return FVDBM_OK;
+        }
+        default: err = "field is not settable"; return FVDBM_ERR_ARG;
+        }
+    }
+
+    int set_params(double tau, double dt) override {
+        if (!(tau > 0)) { err = "tau must be positive"; return FVDBM_ERR_ARG; }
+        P.inv_tau = (real)(1.0 / tau);
+        P.dt = (real)dt;
+        drop_graphs();
+        return FVDBM_OK;
+    }
+
+    int set_option(int opt, int64_t v) override {
+        const int old_variant = variant, old_tile = tile_cells, old_stages = stages, old_graph = graph_steps;
+        switch (opt) {
+        case FVDBM_OPT_VARIANT: variant = v == FVDBM_VARIANT_AUTO ? FVDBM_VARIANT_TMA : (int)v; break;
+        case FVDBM_OPT_TILE_CELLS: tile_cells = (int)v; break;
+        case FVDBM_OPT_STAGES: stages = (int)v; break;
+        case FVDBM_OPT_GRAPH_STEPS: graph_steps = (int)v; break;
+        case FVDBM_OPT_CTAS_PER_SM: ctas_per_sm = (int)v; break;
+        case FVDBM_OPT_REVERSE_SWEEP: reverse_sweep = v ? 1 : 0; break;
+        default: err = "unknown option"; return FVDBM_ERR_ARG;
+        }
+        occ_cache = 0;
+        int rc = sanitize_options();
+        if (rc) { variant = old_variant; tile_cells = old_tile; stages = old_stages; graph_steps = old_graph; return rc; }
+        drop_graphs();
+        return FVDBM_OK;
+    }
+
+    int info(int key, int64_t* v) const override {
+        if (!v) return FVDBM_ERR_ARG;
+        switch (key) {
+        case FVDBM_INFO_MODE: *v = mode; break;
+        case FVDBM_INFO_STEPS: *v = steps; break;
+        case FVDBM_INFO_LAUNCHES: *v = launches; break;
+        case FVDBM_INFO_TRACKED_NODES: *v = plan.NT; break;
+        case FVDBM_INFO_BOUNDARY_SIDES: *v = plan.NB; break;
+        case FVDBM_INFO_DEVICE_BYTES:
+            *v = (int64_t)(pdf[0].bytes() * 2 + ccode.bytes() + ccoef.bytes() + s_cface.bytes() * 2 + s_fcell.bytes() * 2 +
+                           s_fdist.bytes() * 2 + s_fL.bytes() + pos.bytes() + ipos.bytes() + s_flux.bytes() + s_feq.bytes() +
+                           scratch.bytes());
+            break;
+        case FVDBM_INFO_VARIANT: *v = variant; break;
+        case FVDBM_INFO_NPAD: *v = plan.Npad; break;
+        case FVDBM_INFO_FUSED_OK: *v = plan.fused_ok ? 1 : 0; break;
+        case FVDBM_INFO_HALO_CELLS: *v = plan.N - plan.No; break;
+        case FVDBM_INFO_OWNED_CELLS: *v = plan.No; break;
+        default: return FVDBM_ERR_ARG;
+        }
+        return FVDBM_OK;
+    }
+
+    // ---------------------------------------------------------------- halo
+    int halo_set_lists(const int32_t* s, int64_t ns, const int32_t* r, int64_t nr) override {
+        CU_TRY(cudaSetDevice(device));
+        std::vector<int32_t> hs((size_t)ns), hr((size_t)nr);
+        for (int64_t i = 0; i < ns; ++i) {
+            if (s[i] < 0 || s[i] >= plan.N) { err = "send cell out of range"; return FVDBM_ERR_ARG; }
+            hs[i] = plan.pos[s[i]];
+        }
+        for (int64_t i = 0; i < nr; ++i) {
+            if (r[i] < 0 || r[i] >= plan.N) { err = "recv cell out of range"; return FVDBM_ERR_ARG; }
+            hr[i] = plan.pos[r[i]];
+        }
+        CU_TRY(halo_send.upload(hs, stream));
+        CU_TRY(halo_recv.upload(hr, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        return FVDBM_OK;
+    }
+    int halo_pack(void* buf) override {
+        CU_TRY(cudaSetDevice(device));
+        if (halo_send.n == 0) return FVDBM_OK;
+        k_pack<real, Q><<<blocks_for((int64_t)halo_send.n * Q, 256), 256, 0, stream>>>(pdf[cur].p, halo_send.p, (int64_t)halo_send.n,
+                                                                                   static_cast<real*>(buf));
+        ++launches;
+        CU_TRY(cudaGetLastError());
+        return FVDBM_OK;
+    }
+    int halo_unpack(const void* buf) override {
+        CU_TRY(cudaSetDevice(device));
+        if (halo_recv.n == 0) return FVDBM_OK;
+        k_unpack<real, Q><<<blocks_for((int64_t)halo_recv.n * Q, 256), 256, 0, stream>>>(pdf[cur].p, halo_recv.p, (int64_t)halo_recv.n,
+                                                                                     static_cast<const real*>(buf));
+        ++launches;
+        CU_TRY(cudaGetLastError());
+        return FVDBM_OK;
+    }
+    void* stream_handle() override { return (void*)stream; }
+};
+
+template <typename real, int Q, int K>
+Engine* make_scheme(const fvdbm_desc& d, int* rc, std::string* msg) {
+    Engine* e = nullptr;
+    if (d.scheme == FVDBM_SCHEME_UPWIND) {
+        auto* t = new EngineT<real, Q, K, 0>(); *rc = t->init(d); e = t;
+    } else if (d.scheme == FVDBM_SCHEME_LAX_WENDROFF) {
+        auto* t = new EngineT<real, Q, K, 1>(); *rc = t->init(d); e = t;
+    } else { *rc = FVDBM_ERR_ARG; *msg = "Unknown flux scheme"; return nullptr; }
+    if (*rc) { *msg = e->err; delete e; return nullptr; }
+    return e;
+}
+
+template <typename real>
+Engine* make_engine(const fvdbm_desc& d, int* rc, std::string* msg) {
+    if (d.Q == 9 && d.K == 3) return make_scheme<real, 9, 3>(d, rc, msg);
+    if (d.Q == 9 && d.K == 4) return make_scheme<real, 9, 4>(d, rc, msg);
+    if (d.Q == 13 && d.K == 3) return make_scheme<real, 13, 3>(d, rc, msg);
+    if (d.Q == 13 && d.K == 4) return make_scheme<real, 13, 4>(d, rc, msg);
+    *rc = FVDBM_ERR_UNSUPPORTED; *msg = "unsupported (Q,K): Q in {9,13}, K in {3,4}";
+    return nullptr;
+}
+
+struct PlanBox {
+    int dtype = 32;
+    Plan<float> f;
+    Plan<double> d;
+};
+
+}  // namespace
+
+namespace {
+template <typename real>
+int64_t plan_array(const Plan<real>& p, const std::string& k, const void** ptr, int32_t* eb) {
+#define I32(name) if (k == #name) { *ptr = p.name.data(); *eb = 4; return (int64_t)p.name.size(); }
+#define REAL(name) if (k == #name) { *ptr = p.name.data(); *eb = (int32_t)sizeof(real); return (int64_t)p.name.size(); }
+    I32(pos) I32(ipos) I32(ccode) I32(bf_na) I32(bf_nb) I32(tn_orig) I32(tn_type) I32(node_track)
+    I32(ring_off) I32(ring_cell) I32(s_cface) I32(s_csign) I32(s_fcell) I32(s_fnode)
+    REAL(ccoef) REAL(bf_ratio) REAL(ring_w) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel)
+#undef I32
+#undef REAL
+    return -1;
+}
+template <typename real>
+int64_t plan_scalar(const Plan<real>& p, const std::string& k) {
+    if (k == "N") return p.N; if (k == "F") return p.F; if (k == "P") return p.P; if (k == "No") return p.No;
+    if (k == "Npad") return p.Npad; if (k == "Bstart") return p.Bstart; if (k == "Oend") return p.Oend;
+    if (k == "Hstart") return p.Hstart; if (k == "NB") return p.NB; if (k == "NT") return p.NT;
+    if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "NC") return p.NC;
+    if (k == "fused_ok") return p.fused_ok ? 1 : 0;
+    return -1;
+}
+}  // namespace
+
+struct fvdbm_handle { Engine* e; };
+struct fvdbm_plan { PlanBox b; };
+
+extern "C" {
+
+int fvdbm_abi_version(void) { return FVDBM_ABI_VERSION; }
+
+const char* fvdbm_last_error(const fvdbm_handle* h) { return h ? h->e->err.c_str() : g_create_error.c_str(); }
+
+int fvdbm_create(const fvdbm_desc* desc, fvdbm_handle** out) {
+    if (!desc || !out) { g_create_error = "null argument"; return FVDBM_ERR_ARG; }
+    *out = nullptr;
+    if (desc->abi_version != FVDBM_ABI_VERSION) { g_create_error = "abi_version mismatch"; return FVDBM_ERR_ARG; }
+    int rc = FVDBM_OK;
+    std::string msg;
+    Engine* e = nullptr;
+    if (desc->dtype == 32) e = make_engine<float>(*desc, &rc, &msg);
+    else if (desc->dtype == 64) e = make_engine<double>(*desc, &rc, &msg);
+    else { rc = FVDBM_ERR_ARG; msg = "dtype must be 32 or 64"; }
+    if (!e) { g_create_error = msg; return rc ? rc : FVDBM_ERR_ARG; }
+    *out = new fvdbm_handle{e};
+    return FVDBM_OK;
+}
+
+void fvdbm_destroy(fvdbm_handle* h) { if (h) { delete h->e; delete h; } }
+int fvdbm_step(fvdbm_handle* h, int n) { return h ? h->e->step(n) : FVDBM_ERR_ARG; }
+int fvdbm_step_timed(fvdbm_handle* h, int n, float* ms) { return h ? h->e->step_timed(n, ms) : FVDBM_ERR_ARG; }
+int fvdbm_step_phase(fvdbm_handle* h, int phase) { return h ? h->e->step_phase(phase) : FVDBM_ERR_ARG; }
+int fvdbm_sync(fvdbm_handle* h) { return h ? h->e->sync() : FVDBM_ERR_ARG; }
+int fvdbm_get(fvdbm_handle* h, int field, void* dst, size_t bytes) { return h ? h->e->get(field, dst, bytes) : FVDBM_ERR_ARG; }
+int fvdbm_set(fvdbm_handle* h, int field, const void* src, size_t bytes) { return h ? h->e->set(field, src, bytes) : FVDBM_ERR_ARG; }
+int fvdbm_set_params(fvdbm_handle* h, double tau, double dt) { return h ? h->e->set_params(tau, dt) : FVDBM_ERR_ARG; }
+int fvdbm_set_option(fvdbm_handle* h, int opt, int64_t v) { return h ? h->e->set_option(opt, v) : FVDBM_ERR_ARG; }
+int fvdbm_info(const fvdbm_handle* h, int key, int64_t* v) { return h ? h->e->info(key, v) : FVDBM_ERR_ARG; }
+int fvdbm_halo_set_lists(fvdbm_handle* h, const int32_t* s, int64_t ns, const int32_t* r, int64_t nr) {
+    return h ? h->e->halo_set_lists(s, ns, r, nr) : FVDBM_ERR_ARG;
+}
+int fvdbm_halo_pack(fvdbm_handle* h, void* buf) { return h ? h->e->halo_pack(buf) : FVDBM_ERR_ARG; }
+int fvdbm_halo_unpack(fvdbm_handle* h, const void* buf) { return h ? h->e->halo_unpack(buf) : FVDBM_ERR_ARG; }
+void* fvdbm_stream(fvdbm_handle* h) { return h ? h->e->stream_handle() : nullptr; }
+
+// ---- host-only planning -------------------------------------------------------------------------
+int fvdbm_plan_create(const fvdbm_desc* desc, fvdbm_plan** out) {
+    if (!desc || !out) { g_create_error = "null argument"; return FVDBM_ERR_ARG; }
+    *out = nullptr;
+    auto* p = new fvdbm_plan();
+    p->b.dtype = desc->dtype;
+    bool ok = false;
+    if (desc->dtype == 32) { ok = p->b.f.build(*desc); if (!ok) g_create_error = p->b.f.error; }
+    else if (desc->dtype == 64) { ok = p->b.d.build(*desc); if (!ok) g_create_error = p->b.d.error; }
+    else g_create_error = "dtype must be 32 or 64";
+    if (!ok) { delete p; return FVDBM_ERR_ARG; }
+    *out = p;
+    return FVDBM_OK;
+}
+void fvdbm_plan_destroy(fvdbm_plan* p) { delete p; }
+
+int64_t fvdbm_plan_array(const fvdbm_plan* p, const char* key, const void** ptr, int32_t* eb) {
+    if (!p || !key || !ptr || !eb) return -1;
+    return p->b.dtype == 32 ? plan_array(p->b.f, key, ptr, eb) : plan_array(p->b.d, key, ptr, eb);
+}
+int64_t fvdbm_plan_scalar(const fvdbm_plan* p, const char* key) {
+    if (!p || !key) return -1;
+    return p->b.dtype == 32 ? plan_scalar(p->b.f, key) : plan_scalar(p->b.d, key);
+}
+
+}  // extern "C"

@@ -1,2 +1,341 @@
-class Environment:  # placeholder, replaced below
-    pass
+"""Drop-in replacement for the reference ``Environment`` (/root/reference/src/environment.py:10-68).
+
+Same constructor / factories / ``init()`` / ``step()`` / ``__repr__`` and the same attribute surface
+(``env.cells.{pdf,rho,vel,pdf_eq,face_indices,face_normals}``, ``env.faces.{pdf,...}``,
+``env.nodes.{pdf,rho,vel,type,...}``) so the reference notebooks run unchanged, but ``step()``
+enqueues hand-written sm_100a kernels through the C ABI of libfvdbm_b200.so instead of tracing a
+jit.  Differences a caller can observe:
+
+* ``step(n=1)``: optional step count (one C call, CUDA-graph batched); still returns an env
+  (``self``), so ``env = env.step()`` keeps working.
+* dynamic arrays are host NumPy arrays materialised on demand, in the ORIGINAL element numbering
+  and the reference's shapes, with the reference's one-step lag for rho / vel / pdf_eq / flux
+  (SURVEY.md A.2).
+* precision is explicit: ``Environment.dtype`` / ``dtype=`` (float32 like stock JAX, or float64).
+* no CPU fallback: without the CUDA library or a CUDA device ``step()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .containers import Cells, Faces, Nodes
+from .dynamics import Dynamics, D2Q9, D2Q13
+from .reorder import choose_perm
+
+__all__ = ["Environment"]
+
+_LATTICES = {9: D2Q9, 13: D2Q13}
+
+
+def _np(a, dtype=None):
+    """np.asarray that also understands the reference's CustomArray / jax arrays."""
+    if hasattr(a, "data") and hasattr(a, "default_value") and not isinstance(a, np.ndarray):
+        a = a.data
+    return np.asarray(a, dtype=dtype)
+
+
+class _View:
+    """Attribute view over one container: statics are plain arrays, dynamic fields are fetched
+    from the device lazily (cached until the next step) and can be assigned to."""
+    _dynamic: dict = {}
+    _static: tuple = ()
+
+    def __init__(self, env, src):
+        object.__setattr__(self, "_env", env)
+        object.__setattr__(self, "_src", src)
+
+    def __getattr__(self, name):
+        if name in type(self)._dynamic:
+            return self._env._fetch(type(self)._dynamic[name])
+        return getattr(self._src, name)
+
+    def __setattr__(self, name, value):
+        if name in type(self)._dynamic:
+            self._env._store(type(self)._dynamic[name], value)
+        else:
+            setattr(self._src, name, value)
+
+    def init(self):
+        if hasattr(self._src, "init"):
+            self._src.init()
+
+    def __repr__(self):
+        keys = list(type(self)._dynamic) + list(type(self)._static)
+        return repr({k: getattr(self, k) for k in keys})
+
+
+class _CellsView(_View):
+    _dynamic = {"pdf": "cells.pdf", "rho": "cells.rho", "vel": "cells.vel", "pdf_eq": "cells.pdf_eq"}
+    _static = ("face_indices", "face_normals")
+
+
+class _FacesView(_View):
+    _dynamic = {"pdf": "faces.pdf"}
+    _static = ("nodes_index", "stencil_cells_index", "stencil_dists", "n", "L", "flux_scheme")
+
+
+class _NodesView(_View):
+    _dynamic = {"pdf": "nodes.pdf", "rho": "nodes.rho", "vel": "nodes.vel"}
+    _static = ("type", "cells_index", "cell_dists")
+
+
+_FIELD = {"cells.pdf": _lib.CELL_PDF, "cells.rho": _lib.CELL_RHO, "cells.vel": _lib.CELL_VEL,
+          "cells.pdf_eq": _lib.CELL_PDF_EQ, "faces.pdf": _lib.FACE_FLUX, "nodes.pdf": _lib.NODE_PDF,
+          "nodes.rho": _lib.NODE_RHO, "nodes.vel": _lib.NODE_VEL}
+_SETTABLE = ("cells.pdf", "nodes.pdf", "nodes.rho", "nodes.vel")
+
+
+class Environment:
+    """Environment(cells, faces, nodes).init(); env = env.step()"""
+    # class-level knobs, mirroring the reference's class variable ``dynamics`` (environment.py:13)
+    dynamics: Dynamics = None
+    dtype = np.float32          # stock JAX runs this path in float32
+    device = 0
+    reorder = "auto"            # 'auto' | 'hilbert' | 'rcm' | 'none' | explicit permutation
+    mode = "auto"               # 'auto' | 'fused' | 'staged'
+
+    def __init__(self, cells, faces, nodes, dtype=None, device=None, reorder=None, mode=None,
+                 n_owned=0):
+        self._attach(cells, faces, nodes)
+        if dtype is not None:
+            self.dtype = np.dtype(dtype).type
+        if device is not None:
+            self.device = device
+        if reorder is not None:
+            self.reorder = reorder
+        if mode is not None:
+            self.mode = mode
+        self._n_owned = n_owned
+
+    # ------------------------------------------------------------------ factories (environment.py:20-36)
+    @classmethod
+    def create(cls, num_cells, num_faces, num_nodes):
+        temp = cls.__new__(cls)
+        temp._attach(Cells(num_cells, cls.dynamics), Faces(num_faces, cls.dynamics), Nodes(num_nodes, cls.dynamics))
+        temp._n_owned = 0
+        return temp
+
+    @classmethod
+    def define(cls, cells, faces, nodes):
+        temp = cls.__new__(cls)
+        temp._attach(cells, faces, nodes)
+        temp._n_owned = 0
+        return temp
+
+    def _attach(self, cells, faces, nodes):
+        self._handle = None
+        self._lib = None
+        self._steps = 0
+        self._cache = {}
+        self._host = {}
+        self._options = {}
+        self.cells = _CellsView(self, cells)
+        self.faces = _FacesView(self, faces)
+        self.nodes = _NodesView(self, nodes)
+
+    def init(self):
+        """reference environment.py:38-42: finalise the containers (CustomArray -> dense arrays)."""
+        self.cells.init()
+        self.faces.init()
+        self.nodes.init()
+
+    # ------------------------------------------------------------------ engine
+    @property
+    def real(self):
+        return np.dtype(self.dtype)
+
+    def _describe(self):
+        c, f, n = self.cells._src, self.faces._src, self.nodes._src
+        dyn = getattr(c, "dynamics", None) or type(self).dynamics
+        if dyn is None:
+            raise ValueError("no dynamics: pass containers built with a Dynamics or set Environment.dynamics")
+        Q = int(dyn.NUM_QUIVERS)
+        if Q not in _LATTICES or not np.array_equal(np.asarray(dyn.KSI), _LATTICES[Q].KSI):
+            raise ValueError("unsupported lattice: D2Q9 and D2Q13 (reference dynamics.py) are compiled in")
+        real = self.real
+        fi = _np(c.face_indices)
+        K = int(fi.shape[1])
+        N = fi.shape[0]
+        scheme = getattr(f, "flux_scheme", "upwind")
+        stencil = _np(f.stencil_cells_index)
+        host = self._host
+        host["cells.pdf"] = np.array(_np(c.pdf), dtype=real).reshape(N, Q)
+        host["cells.rho"] = np.array(_np(c.rho), dtype=real).reshape(N, 1)
+        host["cells.vel"] = np.array(_np(c.vel), dtype=real).reshape(N, 2)
+        host["cells.pdf_eq"] = np.array(_np(c.pdf_eq), dtype=real).reshape(N, Q)
+        host["faces.pdf"] = np.array(_np(f.pdf), dtype=real).reshape(stencil.shape[0], Q)
+        Pn = _np(n.type).reshape(-1).shape[0]
+        host["nodes.pdf"] = np.array(_np(n.pdf), dtype=real).reshape(Pn, Q)
+        host["nodes.rho"] = np.array(_np(n.rho), dtype=real).reshape(Pn, 1)
+        host["nodes.vel"] = np.array(_np(n.vel), dtype=real).reshape(Pn, 2)
+        perm = choose_perm(self.reorder, N, getattr(c, "centers", None), stencil) if not self._n_owned else \
+            (self.reorder if isinstance(self.reorder, np.ndarray) else None)
+        mode = {"auto": _lib.MODE_AUTO, "fused": _lib.MODE_FUSED, "staged": _lib.MODE_STAGED}[self.mode]
+        return _lib.DescArrays(
+            dtype=real, scheme=scheme, Q=Q, K=K, tau=float(dyn.tau), delta_t=float(dyn.delta_t),
+            lattice_constants=_LATTICES[Q].lattice_constants(real),
+            cell_face_idx=fi, cell_face_sign=_np(c.face_normals), face_cell_idx=stencil,
+            face_dists=_np(f.stencil_dists), face_node_idx=_np(f.nodes_index), face_n=_np(f.n), face_L=_np(f.L),
+            node_type=_np(n.type), node_cell_idx=_np(n.cells_index), node_cell_dist=_np(n.cell_dists),
+            cell_pdf=host["cells.pdf"], node_pdf=host["nodes.pdf"], node_rho=host["nodes.rho"],
+            node_vel=host["nodes.vel"], cell_perm=perm, n_owned=self._n_owned, device_id=self.device, mode=mode)
+
+    def build(self):
+        """Create the device engine (done implicitly by the first ``step``)."""
+        if self._handle is not None:
+            return self
+        lib = _lib.load()                      # raises if the CUDA library is not built
+        da = self._describe()
+        h = C.c_void_p()
+        _lib.check(lib.fvdbm_create(C.byref(da.desc), C.byref(h)))
+        self._lib, self._handle, self._desc_arrays = lib, h, da
+        self._shape = {"cells.pdf": (da.N, da.Q), "cells.rho": (da.N, 1), "cells.vel": (da.N, 2),
+                       "cells.pdf_eq": (da.N, da.Q), "faces.pdf": (da.F, da.Q), "nodes.pdf": (da.P, da.Q),
+                       "nodes.rho": (da.P, 1), "nodes.vel": (da.P, 2)}
+        for k, v in self._options.items():
+            _lib.check(lib.fvdbm_set_option(h, k, v), h)
+        return self
+
+    def step(self, n: int = 1):
+        """n iterations of reference ``Environment.step`` (environment.py:55-65); asynchronous."""
+        self.build()
+        _lib.check(self._lib.fvdbm_step(self._handle, int(n)), self._handle)
+        if n > 0:
+            self._steps += int(n)
+            self._cache.clear()
+        return self
+
+    def step_timed(self, n: int) -> float:
+        """Like ``step(n)`` but blocks and returns the device time in milliseconds (CUDA events)."""
+        self.build()
+        ms = C.c_float()
+        _lib.check(self._lib.fvdbm_step_timed(self._handle, int(n), C.byref(ms)), self._handle)
+        if n > 0:
+            self._steps += int(n)
+            self._cache.clear()
+        return float(ms.value)
+
+    def sync(self):
+        if self._handle is not None:
+            _lib.check(self._lib.fvdbm_sync(self._handle), self._handle)
+        return self
+
+    def set_option(self, option: int, value: int):
+        self._options[option] = int(value)
+        if self._handle is not None:
+            _lib.check(self._lib.fvdbm_set_option(self._handle, option, int(value)), self._handle)
+        return self
+
+    def set_params(self, tau: float, delta_t: float):
+        self.build()
+        _lib.check(self._lib.fvdbm_set_params(self._handle, float(tau), float(delta_t)), self._handle)
+        return self
+
+    def info(self, key: int) -> int:
+        self.build()
+        v = C.c_int64()
+        _lib.check(self._lib.fvdbm_info(self._handle, key, C.byref(v)), self._handle)
+        return int(v.value)
+
+    # ------------------------------------------------------------------ dynamic fields
+    def _fetch(self, name):
+        if self._handle is None:
+            src = {"cells": self.cells, "faces": self.faces, "nodes": self.nodes}[name.split(".")[0]]._src
+            return getattr(src, name.split(".")[1])
+        if name in self._cache:
+            return self._cache[name]
+        lagged = name in ("cells.rho", "cells.vel", "cells.pdf_eq", "faces.pdf")
+        if lagged and self._steps == 0:
+            return self._host[name]
+        shape = self._shape[name]
+        if name.startswith("nodes."):
+            out = np.array(self._host[name], copy=True)          # untracked rows keep their values
+        else:
+            out = np.empty(shape, dtype=self.real)
+        _lib.check(self._lib.fvdbm_get(self._handle, _FIELD[name], out.ctypes.data, out.nbytes), self._handle)
+        if name.startswith("nodes."):
+            self._host[name] = out
+        self._cache[name] = out
+        return out
+
+    def get_into(self, name: str, out: np.ndarray):
+        """Download field ``name`` ("cells.rho", ...) into a caller-owned (e.g. pinned) array."""
+        self.build()
+        if out.dtype != self.real or out.size != int(np.prod(self._shape[name])) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous array of the engine dtype and the field's size")
+        _lib.check(self._lib.fvdbm_get(self._handle, _FIELD[name], out.ctypes.data, out.nbytes), self._handle)
+        return out
+
+    def set_cells_pdf(self, arr: np.ndarray):
+        """Upload populations from a caller-owned (e.g. pinned) (N,Q) array of the engine dtype."""
+        self.build()
+        if arr.dtype != self.real or arr.size != int(np.prod(self._shape["cells.pdf"])) or not arr.flags.c_contiguous:
+            raise ValueError("arr must be a contiguous (N,Q) array of the engine dtype")
+        _lib.check(self._lib.fvdbm_set(self._handle, _lib.CELL_PDF, arr.ctypes.data, arr.nbytes), self._handle)
+        self._cache.pop("cells.pdf", None)
+        return self
+
+    def _store(self, name, value):
+        if self._handle is None:
+            src = {"cells": self.cells, "faces": self.faces, "nodes": self.nodes}[name.split(".")[0]]._src
+            setattr(src, name.split(".")[1], value)
+            return
+        if name not in _SETTABLE:
+            raise AttributeError(f"{name} is derived state (recomputed every step) and cannot be assigned")
+        arr = np.ascontiguousarray(_np(value), dtype=self.real).reshape(self._shape[name])
+        _lib.check(self._lib.fvdbm_set(self._handle, _FIELD[name], arr.ctypes.data, arr.nbytes), self._handle)
+        if name.startswith("nodes."):
+            self._host[name] = np.array(arr, copy=True)
+        self._cache.pop(name, None)
+
+    # ------------------------------------------------------------------ lifetime / pickling
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.fvdbm_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __getstate__(self):
+        """Pickle = download (reference Mesher.to_pickle dumps (env, mesher), mesher.py:600-602)."""
+        c, f, n = self.cells._src, self.faces._src, self.nodes._src
+        dyn = getattr(c, "dynamics", None) or type(self).dynamics
+        dyn_state = (int(dyn.NUM_QUIVERS), float(dyn.tau), float(dyn.delta_t))
+        st = {"dyn": dyn_state, "dtype": np.dtype(self.dtype).str, "device": self.device,
+              "reorder": self.reorder if not isinstance(self.reorder, np.ndarray) else "auto",
+              "mode": self.mode, "steps": self._steps, "n_owned": self._n_owned,
+              "scheme": getattr(f, "flux_scheme", "upwind")}
+        for view in (self.cells, self.faces, self.nodes):
+            pre = {"_CellsView": "cells", "_FacesView": "faces", "_NodesView": "nodes"}[type(view).__name__]
+            for k in type(view)._dynamic:
+                st[f"{pre}.{k}"] = np.array(_np(getattr(view, k)))
+            for k in type(view)._static:
+                if k != "flux_scheme":
+                    st[f"{pre}.{k}"] = np.array(_np(getattr(view._src, k)))
+        if hasattr(c, "centers"):
+            st["cells.centers"] = np.array(c.centers)
+        return st
+
+    def __setstate__(self, st):
+        Q, tau, dt = st["dyn"]
+        dyn = _LATTICES[Q](tau, dt)
+        N, F, Pn = st["cells.pdf"].shape[0], st["faces.pdf"].shape[0], st["nodes.pdf"].shape[0]
+        cells, faces, nodes = Cells(N, dyn), Faces(F, dyn, st["scheme"]), Nodes(Pn, dyn)
+        for key, val in st.items():
+            if "." in key:
+                pre, attr = key.split(".")
+                setattr({"cells": cells, "faces": faces, "nodes": nodes}[pre], attr, val)
+        self._attach(cells, faces, nodes)
+        self.dtype = np.dtype(st["dtype"]).type
+        self.device, self.reorder, self.mode = st["device"], st["reorder"], st["mode"]
+        self._n_owned = st["n_owned"]
+
+    def __repr__(self):
+        return f"Environment(cells={self.cells}, faces={self.faces}, nodes={self.nodes})"

@@ -1,0 +1,53 @@
+"""Pin the oracle: the NumPy restatement (oracle/step_numpy.py) and its C/OpenMP twin
+(oracle/step_c.c) must reproduce the golden vectors that oracle/make_golden.py minted by running
+the reference's own sources (src/environment.py, containers.py, dynamics.py, utils/utils.py)."""
+import numpy as np
+import pytest
+
+import golden
+from oracle.step_c import COracle
+
+
+def _walk(case, oracle, tol):
+    done = 0
+    for s in case.steps:
+        oracle.step(s - done)
+        done = s
+        for k, v in oracle.state().items():
+            assert golden.rel_err(v, case.expected(s, k)) < tol, (case.name, s, k)
+
+
+@pytest.mark.parametrize("name", golden.names())
+def test_numpy_restatement_fp64(name):
+    case = golden.Case(name)
+    _walk(case, case.oracle(np.float64), 1e-13)
+
+
+@pytest.mark.parametrize("name", golden.names())
+def test_c_restatement_fp64(name):
+    case = golden.Case(name)
+    _walk(case, COracle(case.static, case.init, case.Q, case.tau, case.delta_t, case.scheme, np.float64), 1e-13)
+
+
+@pytest.mark.parametrize("name", golden.names(fp32=True))
+def test_restatements_fp32_vs_stock_jax_like_fp32(name):
+    """*_f32 fixtures: the reference run with every float in fp32 (what stock JAX does)."""
+    case = golden.Case(name)
+    _walk(case, case.oracle(np.float32), 2e-6)
+    _walk(case, COracle(case.static, case.init, case.Q, case.tau, case.delta_t, case.scheme, np.float32), 2e-6)
+
+
+def test_rest_state_is_a_fixed_point():
+    case = golden.Case("rest_upwind")
+    o = case.oracle(np.float64).step(3)
+    assert np.max(np.abs(o.pdf - case.init["cells.pdf"])) < 1e-16
+
+
+def test_one_step_lag_of_moments():
+    """after step(), cells.rho is the density of the PDFs *before* the update."""
+    case = golden.Case("ldc_tri_lw")
+    o = case.oracle(np.float64)
+    before = o.pdf.sum(axis=1, keepdims=True)
+    o.step(1)
+    np.testing.assert_allclose(o.rho, before, rtol=1e-15)
+    assert np.max(np.abs(o.rho - o.pdf.sum(axis=1, keepdims=True))) > 1e-9
