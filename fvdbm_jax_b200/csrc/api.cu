@@ -79,7 +79,7 @@ struct EngineT final : Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     int mode = FVDBM_MODE_FUSED;
-    int variant = FVDBM_VARIANT_TMA;
+    int variant = FVDBM_VARIANT_DIRECT;   // measured: 97% of the HBM roofline at 10M cells vs 82-90% for TMA
     int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
     int num_sms = 148;
     int cur = 0;
@@ -179,7 +179,7 @@ struct EngineT final : Engine {
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
-        if (variant == FVDBM_VARIANT_AUTO) variant = FVDBM_VARIANT_TMA;
+        if (variant == FVDBM_VARIANT_AUTO) variant = FVDBM_VARIANT_DIRECT;
         return sanitize_options();
     }
     size_t max_smem = 0;
@@ -501,7 +501,7 @@ struct EngineT final : Engine {
     int set_option(int opt, int64_t v) override {
         const int old_variant = variant, old_tile = tile_cells, old_stages = stages, old_graph = graph_steps;
         switch (opt) {
-        case FVDBM_OPT_VARIANT: variant = v == FVDBM_VARIANT_AUTO ? FVDBM_VARIANT_TMA : (int)v; break;
+        case FVDBM_OPT_VARIANT: variant = v == FVDBM_VARIANT_AUTO ? FVDBM_VARIANT_DIRECT : (int)v; break;
         case FVDBM_OPT_TILE_CELLS: tile_cells = (int)v; break;
         case FVDBM_OPT_STAGES: stages = (int)v; break;
         case FVDBM_OPT_GRAPH_STEPS: graph_steps = (int)v; break;

@@ -269,6 +269,36 @@ class Environment:
         _lib.check(self._lib.fvdbm_get(self._handle, _FIELD[name], out.ctypes.data, out.nbytes), self._handle)
         return out
 
+    # ------------------------------------------------------------------ multi-GPU primitives
+    def halo_set_lists(self, send_cells: np.ndarray, recv_cells: np.ndarray):
+        """Local ids (original local numbering) of the cells packed for / unpacked from peers."""
+        self.build()
+        s = np.ascontiguousarray(send_cells, dtype=np.int32)
+        r = np.ascontiguousarray(recv_cells, dtype=np.int32)
+        _lib.check(self._lib.fvdbm_halo_set_lists(self._handle, s.ctypes.data, s.size, r.ctypes.data, r.size), self._handle)
+        return self
+
+    def halo_pack(self, dev_ptr: int):
+        _lib.check(self._lib.fvdbm_halo_pack(self._handle, C.c_void_p(dev_ptr)), self._handle)
+
+    def halo_unpack(self, dev_ptr: int):
+        _lib.check(self._lib.fvdbm_halo_unpack(self._handle, C.c_void_p(dev_ptr)), self._handle)
+
+    def step_phase(self, phase: int):
+        """phase 0: interior cells (no halo / boundary dependence); phase 1: node kernel + border
+        cells + buffer swap (completes the step)."""
+        self.build()
+        _lib.check(self._lib.fvdbm_step_phase(self._handle, int(phase)), self._handle)
+        if phase == 1:
+            self._steps += 1
+            self._cache.clear()
+        return self
+
+    @property
+    def stream_ptr(self) -> int:
+        self.build()
+        return int(self._lib.fvdbm_stream(self._handle) or 0)
+
     def set_cells_pdf(self, arr: np.ndarray):
         """Upload populations from a caller-owned (e.g. pinned) (N,Q) array of the engine dtype."""
         self.build()

@@ -226,7 +226,9 @@ class Mesher:
     def _marker_mask(self, marker):
         mk = self.point_markers
         if self.point_alias is not None:
-            mk = mk[self.point_alias]
+            # periodic duplicates are never referenced by a face and have no ring: leave them untyped
+            canonical = self.point_alias == np.arange(mk.shape[0])
+            return (mk[self.point_alias] == marker) & canonical
         return mk == marker
 
     def set_vel_node(self, nodes: Nodes, marker: int, velocity):

@@ -158,3 +158,73 @@ def porous_channel(scale: int = 1, seed: int = 0, n_obst: int = 60) -> RawMesh:
     m = masked_domain(nx, ny, lx, ly, inside, seed=seed)
     m.points[:, 0] -= 93.0
     return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# scalable strip decomposition of the synthetic square (multi-GPU weak / strong scaling)
+# ---------------------------------------------------------------------------------------------------
+def _hash_uniform(idx: np.ndarray, seed: int, salt: int) -> np.ndarray:
+    """Counter-based U[0,1): splitmix64 of the global vertex index, so every rank reproduces the
+    same jitter for the vertices it sees without generating the whole grid."""
+    with np.errstate(over="ignore"):
+        z = idx.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15) * np.uint64(2 * seed + salt + 1)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def strip_window(nx: int, ny_total: int, row0: int, row1: int, jitter: float = 0.2, seed: int = 0,
+                 periodic_x: bool = True) -> RawMesh:
+    """Quad rows [row0,row1) of the global ``nx x ny_total`` triangulated square (hash jitter, so the
+    window is bit-identical to the same rows of the whole mesh).  ``cell_gid`` numbers cells as in
+    the whole mesh (2*(J*nx+I)+t); ``point_gid`` likewise for vertices."""
+    rows = row1 - row0
+    xs = np.arange(nx + 1, dtype=np.int64)
+    ys = np.arange(row0, row1 + 1, dtype=np.int64)
+    GX, GY = np.meshgrid(xs, ys)
+    vid = GY * (nx + 1) + GX
+    X = GX.astype(np.float64)
+    Y = GY.astype(np.float64)
+    interior = (GX > 0) & (GX < nx) & (GY > 0) & (GY < ny_total)
+    if jitter > 0:
+        X = X + np.where(interior, (2 * _hash_uniform(vid, seed, 0) - 1) * jitter, 0.0)
+        Y = Y + np.where(interior, (2 * _hash_uniform(vid, seed, 1) - 1) * jitter, 0.0)
+    points = np.stack([X.reshape(-1), Y.reshape(-1)], axis=1)
+
+    def pid(i, j):
+        return (j * (nx + 1) + i).astype(np.int32)
+
+    I, J = np.meshgrid(np.arange(nx), np.arange(rows))
+    I = I.reshape(-1)
+    J = J.reshape(-1)
+    p00, p10, p11, p01 = pid(I, J), pid(I + 1, J), pid(I + 1, J + 1), pid(I, J + 1)
+    even = ((I + J + row0) % 2) == 0
+    t0 = np.where(even[:, None], np.stack([p00, p10, p11], 1), np.stack([p00, p10, p01], 1))
+    t1 = np.where(even[:, None], np.stack([p00, p11, p01], 1), np.stack([p10, p11, p01], 1))
+    elements = np.empty((2 * nx * rows, 3), dtype=np.int32)
+    elements[0::2] = t0
+    elements[1::2] = t1
+    markers = np.zeros((rows + 1, nx + 1), dtype=np.int32)
+    if not periodic_x:
+        markers[:, 0] = LEFT
+        markers[:, -1] = RIGHT
+    if row0 == 0:
+        markers[0, :] = BOTTOM
+    if row1 == ny_total:
+        markers[-1, :] = TOP
+    alias = None
+    if periodic_x:
+        ids = np.arange((nx + 1) * (rows + 1), dtype=np.int32).reshape(rows + 1, nx + 1)
+        ids[:, -1] = ids[:, 0]
+        alias = ids.reshape(-1)
+    faces = unique_edges(elements, points.shape[0], alias)
+    m = RawMesh(points, elements, faces, markers.reshape(-1), alias, (nx, rows))
+    gq = (J + row0).astype(np.int64) * nx + I
+    gid = np.empty(2 * nx * rows, dtype=np.int64)
+    gid[0::2] = 2 * gq
+    gid[1::2] = 2 * gq + 1
+    m.cell_gid = gid
+    m.cell_row = np.repeat(J + row0, 2)
+    m.point_gid = vid.reshape(-1)
+    return m

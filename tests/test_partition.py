@@ -1,0 +1,157 @@
+"""Host-side decomposition logic (no GPU): partitions, local meshes, halo / exchange maps.
+Halo maps are checked against a pure-Python set construction from the same connectivity
+(the reference has no halo maps to compare with)."""
+import numpy as np
+import pytest
+
+import fvdbm_jax_b200 as fb
+from fvdbm_jax_b200 import meshgen
+from fvdbm_jax_b200.partition import (GlobalMesh, edge_cut, exchange_lists, extract_local, halo_requests,
+                                      partition_sfc, partition_strips, refine_partition)
+from fvdbm_jax_b200.reorder import hilbert_perm, rcm_perm, order_to_perm
+
+
+def problem(nx=14, ny=10, periodic=False, seed=3):
+    raw = meshgen.triangulated_square(nx, ny, seed=seed, periodic_x=periodic)
+    m = fb.Mesher()
+    m.import_meshpy(raw)
+    m.calc_mesh_properties()
+    dyn = fb.D2Q9(0.8, 0.1)
+    cells, faces, nodes = m.to_env(dyn, "lax_wendroff")
+    for mk in ((1,) if periodic else (1, 2, 4)):
+        nodes = m.set_vel_node(nodes, mk, np.array([0.0, 0.0]))
+    nodes = m.set_vel_node(nodes, 3, np.array([0.1, 0.0]))
+    return m, dyn, GlobalMesh.from_containers(cells, faces, nodes)
+
+
+def python_halo(g, part, rank):
+    """Set-based restatement of the halo definition in partition.py's docstring."""
+    owned = {c for c in range(g.num_cells) if part[c] == rank}
+    halo = set()
+    bnodes = set()
+    for c in owned:
+        for j in g.face_indices[c]:
+            a, b = g.stencil[j]
+            for o in (a, b):
+                if o >= 0 and o not in owned:
+                    halo.add(int(o))
+            if a < 0 or b < 0:
+                bnodes.update(int(x) for x in g.nodes_index[j])
+    for p in bnodes:
+        if g.node_type[p, 0] != 0:
+            for c, d in zip(g.ring[p], g.ring_dists[p]):
+                if c >= 0 and d > 0 and c not in owned:
+                    halo.add(int(c))
+    return owned, halo
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("nparts,method", [(2, "strips"), (3, "sfc"), (4, "sfc")])
+def test_local_meshes_and_exchange_maps(periodic, nparts, method):
+    m, dyn, g = problem(periodic=periodic)
+    part = partition_strips(g.centers, nparts) if method == "strips" else partition_sfc(g.centers, nparts)
+    assert np.bincount(part, minlength=nparts).min() >= g.num_cells // nparts - 1          # balanced
+    locals_ = [extract_local(g, part, r) for r in range(nparts)]
+    reqs = [halo_requests(l) for l in locals_]
+    covered = np.zeros(g.num_cells, dtype=int)
+    for r, l in enumerate(locals_):
+        owned, halo = python_halo(g, part, r)
+        assert set(l.cell_gid[:l.n_owned].tolist()) == owned
+        assert set(l.cell_gid[l.n_owned:].tolist()) == halo
+        covered[l.cell_gid[:l.n_owned]] += 1
+        # halo sorted by (owner, gid); owners correct
+        assert np.array_equal(l.halo_owner, part[l.cell_gid[l.n_owned:]])
+        key = l.halo_owner.astype(np.int64) * g.num_cells + l.cell_gid[l.n_owned:]
+        assert np.all(np.diff(key) > 0)
+        # local connectivity maps back to the global one
+        lm = l.mesh
+        for lc in range(l.n_owned):
+            gc = l.cell_gid[lc]
+            assert np.array_equal(l.face_gid[lm.face_indices[lc]], g.face_indices[gc])
+            assert np.array_equal(lm.face_signs[lc], g.face_signs[gc])
+        for lf, gf in enumerate(l.face_gid):
+            for s in range(2):
+                gc = g.stencil[gf, s]
+                lc = lm.stencil[lf, s]
+                assert (gc < 0 and lc < 0) or l.cell_gid[lc] == gc
+            assert np.array_equal(l.node_gid[lm.nodes_index[lf]], g.nodes_index[gf])
+        # complete nodes keep type and their whole ring, incomplete ones are demoted
+        for ln, gn in enumerate(l.node_gid):
+            if l.node_complete[ln]:
+                assert lm.node_type[ln, 0] == g.node_type[gn, 0] != 0
+                valid = g.ring[gn] >= 0
+                assert np.array_equal(l.cell_gid[lm.ring[ln][valid]], g.ring[gn][valid])
+                assert np.array_equal(lm.ring_dists[ln], g.ring_dists[gn])
+            else:
+                assert lm.node_type[ln, 0] == 0
+        # storage permutation keeps owned cells in front
+        assert l.perm is not None and sorted(l.perm.tolist()) == list(range(l.n_local))
+        assert np.all(l.perm[:l.n_owned] < l.n_owned)
+    assert np.all(covered == 1)
+    # every active boundary node is complete on at least one rank
+    active = set(np.nonzero(g.node_type[:, 0] != 0)[0].tolist())
+    complete = set()
+    for l in locals_:
+        complete.update(l.node_gid[l.node_complete].tolist())
+    bn = set()
+    for j in range(g.stencil.shape[0]):
+        if (g.stencil[j] < 0).any():
+            bn.update(g.nodes_index[j].tolist())
+    assert active & bn <= complete
+    # exchange lists: what r sends to s is exactly what s expects from r, in the same order
+    ex = []
+    for r, l in enumerate(locals_):
+        from_peers = {s: reqs[s][r] for s in range(nparts) if r in reqs[s]}
+        ex.append(exchange_lists(l, from_peers))
+    for r, (ps, sc, scnt, pr, rc, rcnt) in enumerate(ex):
+        off = 0
+        for peer, cnt in zip(ps, scnt):
+            sent_gids = locals_[r].cell_gid[sc[off:off + cnt]]
+            pps, _, _, ppr, prc, prcnt = ex[peer]
+            o2 = sum(c for p, c in zip(ppr, prcnt) if p < r)
+            k = ppr.index(r)
+            got_gids = locals_[peer].cell_gid[prc[o2:o2 + prcnt[k]]]
+            assert np.array_equal(sent_gids, got_gids)
+            assert np.all(sc[off:off + cnt] < locals_[r].n_owned)
+            off += cnt
+        assert np.all(rc >= locals_[r].n_owned)
+
+
+def test_refinement_reduces_cut_and_keeps_balance():
+    m, dyn, g = problem(nx=30, ny=30)
+    rng = np.random.default_rng(0)
+    part = partition_sfc(g.centers, 4)
+    noisy = part.copy()
+    flip = rng.random(part.size) < 0.05
+    noisy[flip] = rng.integers(0, 4, flip.sum())
+    refined = refine_partition(g.stencil, noisy, 4, sweeps=6)
+    assert edge_cut(g.stencil, refined) < edge_cut(g.stencil, noisy)
+    sizes = np.bincount(refined, minlength=4)
+    assert sizes.max() <= 1.03 * part.size / 4 + 2
+
+
+def test_reorder_permutations_are_bijections_and_local():
+    m, dyn, g = problem(nx=40, ny=40)
+    n = g.num_cells
+    for perm in (hilbert_perm(g.centers), rcm_perm(g.stencil, n)):
+        assert sorted(perm.tolist()) == list(range(n))
+        st = g.stencil[(g.stencil >= 0).all(axis=1)]
+        span = np.abs(perm[st[:, 0]].astype(np.int64) - perm[st[:, 1]])
+        rnd = np.random.default_rng(0).permutation(n)
+        span_rnd = np.abs(rnd[st[:, 0]].astype(np.int64) - rnd[st[:, 1]])
+        assert np.median(span) * 20 < np.median(span_rnd)            # neighbours stay close in memory
+    # RCM agrees with scipy on its own output being a valid ordering of the same graph
+    order = np.argsort(rcm_perm(g.stencil, n))
+    assert np.array_equal(order_to_perm(order), rcm_perm(g.stencil, n))
+
+
+def test_strip_window_is_bitwise_window_of_whole_mesh():
+    nx, ny = 9, 12
+    whole = meshgen.strip_window(nx, ny, 0, ny)
+    win = meshgen.strip_window(nx, ny, 3, 8)
+    pg = {int(g): i for i, g in enumerate(whole.point_gid)}
+    idx = np.array([pg[int(g)] for g in win.point_gid])
+    assert np.array_equal(whole.points[idx], win.points)
+    cg = {int(g): i for i, g in enumerate(whole.cell_gid)}
+    for lc, g in enumerate(win.cell_gid):
+        assert np.array_equal(whole.point_gid[whole.elements[cg[int(g)]]], win.point_gid[win.elements[lc]])
