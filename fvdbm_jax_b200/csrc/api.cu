@@ -77,7 +77,10 @@ struct EngineT final : Engine {
     Plan<real> plan;
     Params<real> P{};
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // main stream (highest priority): nodes, border cells, transfers
+    cudaStream_t stream2 = nullptr;     // side stream (lowest priority): interior cells, forked/joined per step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap = 1;
     int mode = FVDBM_MODE_FUSED;
     int variant = FVDBM_VARIANT_DIRECT;   // measured: 97% of the HBM roofline at 10M cells vs 82-90% for TMA
     int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
@@ -99,7 +102,10 @@ struct EngineT final : Engine {
     ~EngineT() override {
         cudaSetDevice(device);
         drop_graphs();
+        if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
         if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
     void drop_graphs() {
         for (auto& g : graphs) cudaGraphExecDestroy(g.second);
@@ -128,7 +134,13 @@ struct EngineT final : Engine {
         cudaDeviceProp prop;
         CU_TRY(cudaGetDeviceProperties(&prop, device));
         num_sms = prop.multiProcessorCount;
-        CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU_TRY(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+        CU_TRY(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
+        CU_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        if (const char* e = getenv("FVDBM_OVERLAP")) overlap = atoi(e);
         fill_params(d);
         mode = d.mode == FVDBM_MODE_STAGED ? FVDBM_MODE_STAGED : FVDBM_MODE_FUSED;
         if (mode == FVDBM_MODE_FUSED && !plan.fused_ok) {
@@ -221,11 +233,11 @@ struct EngineT final : Engine {
         return FVDBM_OK;
     }
 
-    int launch_fused(int64_t begin, int64_t end) {
+    int launch_fused(int64_t begin, int64_t end, cudaStream_t st) {
         if (end <= begin) return FVDBM_OK;
         FusedArgs<real> a = fused_args(begin, end);
         if (variant == FVDBM_VARIANT_DIRECT) {
-            k_fused_direct<real, Q, K, SCHEME><<<blocks_for(end - begin, 256), 256, 0, stream>>>(a);
+            k_fused_direct<real, Q, K, SCHEME><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
         } else {
             const size_t smem = kTmaHeader + (size_t)stages * tma_stage_bytes<real, Q, K, SCHEME>(tile_cells);
             int per_sm = ctas_per_sm;
@@ -239,7 +251,7 @@ struct EngineT final : Engine {
             const int64_t ntiles = (end - begin) / tile_cells;
             int64_t grid = (int64_t)num_sms * per_sm;
             if (grid > ntiles) grid = ntiles;
-            k_fused_tma<real, Q, K, SCHEME><<<(unsigned)grid, tile_cells, smem, stream>>>(a, stages);
+            k_fused_tma<real, Q, K, SCHEME><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
         }
         ++launches;
         CU_TRY(cudaGetLastError());
@@ -288,12 +300,31 @@ struct EngineT final : Engine {
 
     int64_t owned_end() const { return round_up(plan.Oend, PAD_TO); }
 
+    // interior cells on the side stream (forked from / joined into the main stream)
+    int fork_interior() {
+        if (plan.Bstart == 0) { phase0_done = true; return FVDBM_OK; }
+        if (!overlap) { int rc = launch_fused(0, plan.Bstart, stream); phase0_done = true; return rc; }
+        CU_TRY(cudaEventRecord(ev_fork, stream));
+        CU_TRY(cudaStreamWaitEvent(stream2, ev_fork, 0));
+        int rc = launch_fused(0, plan.Bstart, stream2);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(ev_join, stream2));
+        phase0_done = true;
+        forked = true;
+        return FVDBM_OK;
+    }
+    bool forked = false;
+
+    // One iteration: interior cells run concurrently with [node kernel -> border cells]; the caller may
+    // have issued the interior part earlier (step_phase(0)) to overlap it with a halo exchange.
     int step_fused_once() {
         int rc;
-        if (!phase0_done && (rc = launch_fused(0, plan.Bstart))) return rc;
-        phase0_done = false;
+        if (!phase0_done && (rc = fork_interior())) return rc;
         if ((rc = launch_nodes())) return rc;
-        if ((rc = launch_fused(plan.Bstart, owned_end()))) return rc;
+        if ((rc = launch_fused(plan.Bstart, owned_end(), stream))) return rc;
+        if (forked) CU_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
+        forked = false;
+        phase0_done = false;
         cur ^= 1; ++steps;
         return FVDBM_OK;
     }
@@ -305,10 +336,7 @@ struct EngineT final : Engine {
         if (mode != FVDBM_MODE_FUSED) { err = "step_phase needs the fused mode"; return FVDBM_ERR_STATE; }
         if (phase == 0) {
             if (phase0_done) { err = "phase 0 already issued"; return FVDBM_ERR_STATE; }
-            int rc = launch_fused(0, plan.Bstart);
-            if (rc) return rc;
-            phase0_done = true;
-            return FVDBM_OK;
+            return fork_interior();
         }
         if (phase == 1) return step_fused_once();
         err = "phase must be 0 or 1";
@@ -403,24 +431,32 @@ struct EngineT final : Engine {
             if (bytes != elems * sizeof(real)) { err = "size mismatch for field"; return false; }
             return true;
         };
+        // cell fields may also be fetched for the owned prefix only ([0,N_owned) rows)
+        int64_t rows = N;
+        auto expect_cells = [&](size_t per) {
+            if (bytes == (size_t)N * per * sizeof(real)) { rows = N; return true; }
+            if (bytes == (size_t)plan.No * per * sizeof(real)) { rows = plan.No; return true; }
+            err = "size mismatch for field";
+            return false;
+        };
         int rc;
         switch (field) {
         case FVDBM_CELL_PDF: case FVDBM_CELL_PDF_PREV: {
-            if (!expect((size_t)N * Q)) return FVDBM_ERR_ARG;
+            if (!expect_cells(Q)) return FVDBM_ERR_ARG;
             if (field == FVDBM_CELL_PDF_PREV && steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
             if ((rc = need_scratch((size_t)N * Q))) return rc;
             const real* src = pdf[field == FVDBM_CELL_PDF ? cur : cur ^ 1].p;
-            k_export_cells<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(src, pos.p, N, scratch.p);
+            k_export_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(src, pos.p, rows, scratch.p);
             ++launches;
             break;
         }
         case FVDBM_CELL_RHO: case FVDBM_CELL_VEL: case FVDBM_CELL_PDF_EQ: {
             const size_t per = field == FVDBM_CELL_RHO ? 1 : field == FVDBM_CELL_VEL ? 2 : Q;
-            if (!expect((size_t)N * per)) return FVDBM_ERR_ARG;
+            if (!expect_cells(per)) return FVDBM_ERR_ARG;
             if (steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
             if ((rc = need_scratch((size_t)N * per))) return rc;
-            k_export_moments<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(
-                P, pdf[cur ^ 1].p, pos.p, N, field == FVDBM_CELL_RHO ? scratch.p : nullptr,
+            k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(
+                P, pdf[cur ^ 1].p, pos.p, rows, field == FVDBM_CELL_RHO ? scratch.p : nullptr,
                 field == FVDBM_CELL_VEL ? scratch.p : nullptr, field == FVDBM_CELL_PDF_EQ ? scratch.p : nullptr);
             ++launches;
             break;
@@ -461,16 +497,14 @@ struct EngineT final : Engine {
         int rc;
         switch (field) {
         case FVDBM_CELL_PDF: {
-            if (bytes != (size_t)N * Q * sizeof(real)) { err = "size mismatch for field"; return FVDBM_ERR_ARG; }
+            int64_t rows = N;                 // all local cells, or only the owned prefix
+            if (bytes == (size_t)plan.No * Q * sizeof(real)) rows = plan.No;
+            else if (bytes != (size_t)N * Q * sizeof(real)) { err = "size mismatch for field"; return FVDBM_ERR_ARG; }
             if ((rc = need_scratch((size_t)N * Q))) return rc;
             CU_TRY(cudaMemcpyAsync(scratch.p, src, bytes, cudaMemcpyHostToDevice, stream));
-            k_import_cells<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(pdf[cur].p, pos.p, N, scratch.p);
+            k_import_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[cur].p, pos.p, rows, scratch.p);
             ++launches;
             CU_TRY(cudaGetLastError());
-            if (plan.No < plan.N) {     // halo copies must be valid in both ping-pong buffers
-                k_import_cells<real, Q><<<blocks_for(N, 256), 256, 0, stream>>>(pdf[cur ^ 1].p, pos.p, N, scratch.p);
-                ++launches;
-            }
             CU_TRY(cudaStreamSynchronize(stream));
             return FVDBM_OK;
         }

@@ -5,7 +5,7 @@
 // Device layout produced here (DESIGN.md "Data layout in HBM"):
 //   * cells live at "positions" pos[i] in [0,Npad); positions are grouped
 //       [ interior | pad | border | pad | halo | pad ],  every group starting on a PAD_TO boundary;
-//     single-GPU handles have no halo and put every cell in the border group (Bstart = 0).
+//     border = owned cells with a boundary side or a halo neighbour (O(sqrt N)); interior = the rest.
 //   * populations are tiled AoSoA: value (cell p, population q) at (p>>5)*(Q*32) + q*32 + (p&31),
 //     so a warp reads 128 contiguous bytes per population and any CTA tile (multiple of 32 cells)
 //     is one contiguous block for cp.async.bulk.
@@ -118,7 +118,10 @@ struct Plan {
         const bool has_halo = No < N;
         if (has_halo && !fused_ok) return fail("halo handles need a consistent mesh: " + why_not);
         int64_t p = 0;
-        if (has_halo) {
+        if (fused_ok) {
+            // interior = owned cells whose K sides are all interior faces to owned cells: they need neither
+            // node values nor halo copies, so the engine updates them concurrently with the exchange /
+            // node kernel / border update (api.cu: step_fused_once).
             std::vector<uint8_t> border(N, 0);
             for (int64_t c = 0; c < No; ++c)
                 for (int k = 0; k < K; ++k) {

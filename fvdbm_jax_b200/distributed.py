@@ -60,15 +60,18 @@ class HaloComm:
 
     def start(self, send_buf, recv_buf):
         import torch.distributed as dist
-        ops, off = [], 0
-        for peer, cnt in zip(self.peers_send, self.send_counts):
-            ops.append(dist.P2POp(dist.isend, send_buf[off:off + cnt], peer))
-            off += cnt
-        off = 0
-        for peer, cnt in zip(self.peers_recv, self.recv_counts):
-            ops.append(dist.P2POp(dist.irecv, recv_buf[off:off + cnt], peer))
-            off += cnt
-        return dist.batch_isend_irecv(ops) if ops else []
+        key = (send_buf.data_ptr(), recv_buf.data_ptr())
+        if getattr(self, "_key", None) != key:            # the op list is reused every iteration
+            ops, off = [], 0
+            for peer, cnt in zip(self.peers_send, self.send_counts):
+                ops.append(dist.P2POp(dist.isend, send_buf[off:off + cnt], peer))
+                off += cnt
+            off = 0
+            for peer, cnt in zip(self.peers_recv, self.recv_counts):
+                ops.append(dist.P2POp(dist.irecv, recv_buf[off:off + cnt], peer))
+                off += cnt
+            self._ops, self._key = ops, key
+        return dist.batch_isend_irecv(self._ops) if self._ops else []
 
     @staticmethod
     def finish(works):
@@ -259,16 +262,11 @@ class DistributedEnvironment:
         return self
 
     def get_into(self, name, out):
-        """Owned rows of a local field into ``out`` ((n_owned, width), e.g. pinned)."""
-        full = getattr(self.env, name.split(".")[0])
-        arr = getattr(full, name.split(".")[1])
-        out[...] = arr[:self.n_owned].reshape(out.shape)
-        return out
+        """Owned rows of a local cell field straight into ``out`` ((n_owned, width), e.g. pinned)."""
+        return self.env.get_into(name, out)
 
     def set_cells_pdf(self, owned_pdf: np.ndarray):
-        cur = np.array(self.env.cells.pdf, copy=True)
-        cur[:self.n_owned] = owned_pdf
-        self.env.set_cells_pdf(np.ascontiguousarray(cur))
+        self.env.set_cells_pdf(owned_pdf)
         return self
 
     def close(self):

@@ -264,8 +264,10 @@ class Environment:
     def get_into(self, name: str, out: np.ndarray):
         """Download field ``name`` ("cells.rho", ...) into a caller-owned (e.g. pinned) array."""
         self.build()
-        if out.dtype != self.real or out.size != int(np.prod(self._shape[name])) or not out.flags.c_contiguous:
-            raise ValueError("out must be a contiguous array of the engine dtype and the field's size")
+        full = int(np.prod(self._shape[name]))
+        owned = self._n_owned * self._shape[name][1] if (self._n_owned and name.startswith("cells.")) else full
+        if out.dtype != self.real or out.size not in (full, owned) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous array of the engine dtype holding all (or all owned) rows")
         _lib.check(self._lib.fvdbm_get(self._handle, _FIELD[name], out.ctypes.data, out.nbytes), self._handle)
         return out
 
@@ -302,8 +304,10 @@ class Environment:
     def set_cells_pdf(self, arr: np.ndarray):
         """Upload populations from a caller-owned (e.g. pinned) (N,Q) array of the engine dtype."""
         self.build()
-        if arr.dtype != self.real or arr.size != int(np.prod(self._shape["cells.pdf"])) or not arr.flags.c_contiguous:
-            raise ValueError("arr must be a contiguous (N,Q) array of the engine dtype")
+        full = int(np.prod(self._shape["cells.pdf"]))
+        owned = self._n_owned * self._shape["cells.pdf"][1] if self._n_owned else full
+        if arr.dtype != self.real or arr.size not in (full, owned) or not arr.flags.c_contiguous:
+            raise ValueError("arr must be a contiguous (N,Q) or (N_owned,Q) array of the engine dtype")
         _lib.check(self._lib.fvdbm_set(self._handle, _lib.CELL_PDF, arr.ctypes.data, arr.nbytes), self._handle)
         self._cache.pop("cells.pdf", None)
         return self
