@@ -182,7 +182,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-nx", type=int, default=1000)
     ap.add_argument("--ref-inner", type=int, default=10)
-    ap.add_argument("--sweep", action="store_true", help="print one extra JSON line per kernel configuration")
+    ap.add_argument("--torch-exchange", action="store_true",
+                    help="N>1: drive the halo exchange from Python with torch.distributed P2P instead of the engine's own NCCL communicator")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -195,6 +196,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    out_fd = os.dup(1)                 # NCCL prints its version banner on stdout: keep stdout clean for
+    os.dup2(2, 1)                      # the single JSON line by routing everything else to stderr
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -204,7 +207,7 @@ def main():
     if world > 1:
         from fvdbm_jax_b200.distributed import DistributedEnvironment
         denv = DistributedEnvironment.weak_scaling_square(args.nx, args.scheme, real, rank, world, local,
-                                                          reorder=args.reorder)
+                                                          reorder=args.reorder, native=not args.torch_exchange)
         env, n_local, n_global = denv, denv.n_owned, denv.n_global
         stepper = denv
     else:
@@ -277,19 +280,29 @@ def main():
                "d2h_bytes_per_step": int((rho_out.numel() + vel_out.numel()) * rho_out.element_size()),
                "note": f"Environment: cells.pdf <- pinned host; step({inner}); cells.rho, cells.vel -> pinned host; per GPU"}
 
-    if rank != 0:
-        return
+    if world > 1:
+        # explicit teardown: engine communicator first, then a barrier so nobody tears NCCL down under
+        # a peer; os._exit skips interpreter-exit destructors that could block on a departed peer
+        import torch.distributed as dist
+        n_launch_info = stepper.info(_lib.INFO_VARIANT)
+        f_over_n_dist = denv.faces_per_cell
+        stepper.close()
+        dist.barrier()
+        if rank != 0:
+            sys.stderr.flush()
+            os._exit(0)
     per_cell, per_face = B_ALG[(args.dtype, args.scheme)]
     if world == 1:
         f_over_n = faces.n.shape[0] / n_local
+        n_launch_info = stepper.info(_lib.INFO_VARIANT)
     else:
-        f_over_n = denv.faces_per_cell
+        f_over_n = f_over_n_dist
     b_alg = per_cell + per_face * f_over_n
     peak, peak_src = measured_peak()
     iter_ms = ms / (inner * args.steps)
     achieved = n_local * b_alg / (iter_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_fused_tma" if stepper.info(_lib.INFO_VARIANT) == 2 else "k_fused_direct",
+                "traffic": None, "kernel": "k_fused_tma" if n_launch_info == 2 else "k_fused_direct",
                 "algorithmic_bytes_per_cell_update": b_alg, "cells_per_launch": n_local, "avg_launch_ms": iter_ms,
                 "peak_source": peak_src,
                 "note": "avg_launch_ms = event time / iterations (includes the O(sqrt N) node kernel); traffic from "
@@ -307,7 +320,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.scheme)
-    print(json.dumps(line))
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

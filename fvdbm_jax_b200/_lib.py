@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfvdbm_b200.so")
 
 ABI_VERSION = 1
+COMM_ID_BYTES = 128
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 SCHEME_UPWIND, SCHEME_LAX_WENDROFF = 0, 1
 MODE_AUTO, MODE_STAGED, MODE_FUSED = 0, 1, 2
@@ -28,7 +29,8 @@ VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA = 0, 1, 2
 EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_error", "fvdbm_step",
            "fvdbm_step_timed", "fvdbm_sync", "fvdbm_get", "fvdbm_set", "fvdbm_set_params",
            "fvdbm_set_option", "fvdbm_info", "fvdbm_halo_set_lists", "fvdbm_halo_pack",
-           "fvdbm_halo_unpack", "fvdbm_step_phase", "fvdbm_stream", "fvdbm_plan_create",
+           "fvdbm_halo_unpack", "fvdbm_step_phase", "fvdbm_stream", "fvdbm_comm_unique_id", "fvdbm_comm_init",
+           "fvdbm_halo_set_peers", "fvdbm_plan_create",
            "fvdbm_plan_destroy", "fvdbm_plan_array", "fvdbm_plan_scalar")
 
 
@@ -81,6 +83,12 @@ def load():
     lib.fvdbm_halo_set_lists.argtypes = [H, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
     lib.fvdbm_halo_pack.argtypes = [H, C.c_void_p]
     lib.fvdbm_halo_unpack.argtypes = [H, C.c_void_p]
+    lib.fvdbm_comm_unique_id.argtypes = [C.c_void_p]
+    lib.fvdbm_comm_unique_id.restype = C.c_int
+    lib.fvdbm_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    lib.fvdbm_comm_init.restype = C.c_int
+    lib.fvdbm_halo_set_peers.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.fvdbm_halo_set_peers.restype = C.c_int
     lib.fvdbm_stream.argtypes = [H]
     lib.fvdbm_stream.restype = C.c_void_p
     lib.fvdbm_plan_create.argtypes = [C.POINTER(Desc), C.POINTER(P)]

@@ -8,6 +8,16 @@
 #include <vector>
 #include <map>
 
+#include <dlfcn.h>
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#else   // minimal declarations (ABI-stable subset) when the header is absent at build time
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclFloat32 = 7, ncclFloat64 = 8 } ncclDataType_t;
+#endif
+
 #include "../../include/fvdbm_b200.h"
 #include "plan.hpp"
 #include "kernels.cuh"
@@ -17,6 +27,38 @@ using namespace fvdbm;
 namespace {
 
 thread_local std::string g_create_error;
+
+// NCCL entry points resolved at run time (torch's bundled libnccl.so.2 if already loaded, else the
+// system one), so libfvdbm_b200.so itself has no link-time NCCL dependency.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {getenv("FVDBM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n) continue;
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { error = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) { error = "missing symbol " name; lib = nullptr; return false; }
+        NCCL_SYM(GetUniqueId, "ncclGetUniqueId") NCCL_SYM(CommInitRank, "ncclCommInitRank") NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv") NCCL_SYM(GroupStart, "ncclGroupStart") NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
 
 struct Engine {
     virtual ~Engine() {}
@@ -34,6 +76,8 @@ struct Engine {
     virtual int halo_pack(void* buf) = 0;
     virtual int halo_unpack(const void* buf) = 0;
     virtual void* stream_handle() = 0;
+    virtual int comm_init(int nranks, int rank, const void* id) = 0;
+    virtual int halo_set_peers(const int32_t* sp, const int64_t* sc, int ns, const int32_t* rp, const int64_t* rc, int nr) = 0;
 };
 
 #define CU_TRY(expr)                                                                          \
@@ -97,11 +141,18 @@ struct EngineT final : Engine {
     DevBuf<real> s_rho, s_ux, s_uy, s_feq, s_flux;     // staged dynamics (lazy)
     DevBuf<real> scratch;                              // export/import staging
     DevBuf<int32_t> halo_send, halo_recv;
+    // native exchange (optional)
+    ncclComm_t comm = nullptr;
+    std::vector<int> send_peers, recv_peers;
+    std::vector<int64_t> send_counts, recv_counts;
+    DevBuf<real> sendbuf, recvbuf;
+    bool native_exchange() const { return comm != nullptr && (!send_peers.empty() || !recv_peers.empty()); }
     std::map<int, cudaGraphExec_t> graphs;             // key: starting `cur`
 
     ~EngineT() override {
         cudaSetDevice(device);
         drop_graphs();
+        if (comm && g_nccl.CommDestroy) { cudaStreamSynchronize(stream); g_nccl.CommDestroy(comm); }
         if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
         if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -319,13 +370,75 @@ struct EngineT final : Engine {
     // have issued the interior part earlier (step_phase(0)) to overlap it with a halo exchange.
     int step_fused_once() {
         int rc;
-        if (!phase0_done && (rc = fork_interior())) return rc;
+        const bool xchg = native_exchange();
+        if (xchg && phase0_done) { err = "step_phase(0) cannot be combined with the native exchange"; return FVDBM_ERR_STATE; }
+        if (!phase0_done && (rc = fork_interior())) return rc;       // fork first: the exchange must not delay it
+        if (xchg && (rc = exchange())) return rc;
         if ((rc = launch_nodes())) return rc;
         if ((rc = launch_fused(plan.Bstart, owned_end(), stream))) return rc;
         if (forked) CU_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
         forked = false;
         phase0_done = false;
         cur ^= 1; ++steps;
+        return FVDBM_OK;
+    }
+
+#define NCCL_TRY(expr)                                                                        \
+    do {                                                                                      \
+        ncclResult_t r_ = (expr);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            err = std::string(#expr) + ": " + g_nccl.GetErrorString(r_);                      \
+            return FVDBM_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+    // pack -> grouped ncclSend/ncclRecv with every neighbour -> unpack, all on the main stream
+    // (the interior update is already running on the side stream)
+    int exchange() {
+        int rc;
+        if ((rc = halo_pack(sendbuf.p))) return rc;
+        const ncclDataType_t dt = sizeof(real) == 4 ? ncclFloat32 : ncclFloat64;
+        NCCL_TRY(g_nccl.GroupStart());
+        size_t off = 0;
+        for (size_t i = 0; i < send_peers.size(); ++i) {
+            NCCL_TRY(g_nccl.Send(sendbuf.p + off * Q, (size_t)send_counts[i] * Q, dt, send_peers[i], comm, stream));
+            off += (size_t)send_counts[i];
+        }
+        off = 0;
+        for (size_t i = 0; i < recv_peers.size(); ++i) {
+            NCCL_TRY(g_nccl.Recv(recvbuf.p + off * Q, (size_t)recv_counts[i] * Q, dt, recv_peers[i], comm, stream));
+            off += (size_t)recv_counts[i];
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+        launches += 1;
+        return halo_unpack(recvbuf.p);
+    }
+
+    int comm_init(int nranks, int rank, const void* id) override {
+        CU_TRY(cudaSetDevice(device));
+        if (!id || nranks < 1 || rank < 0 || rank >= nranks) { err = "bad communicator arguments"; return FVDBM_ERR_ARG; }
+        if (!g_nccl.load()) { err = g_nccl.error; return FVDBM_ERR_CUDA; }
+        if (comm) { g_nccl.CommDestroy(comm); comm = nullptr; }
+        ncclUniqueId uid;
+        memcpy(&uid, id, sizeof(uid));
+        NCCL_TRY(g_nccl.CommInitRank(&comm, nranks, uid, rank));
+        drop_graphs();
+        return FVDBM_OK;
+    }
+
+    int halo_set_peers(const int32_t* sp, const int64_t* sc, int ns, const int32_t* rp, const int64_t* rc, int nr) override {
+        CU_TRY(cudaSetDevice(device));
+        int64_t tot_s = 0, tot_r = 0;
+        for (int i = 0; i < ns; ++i) tot_s += sc[i];
+        for (int i = 0; i < nr; ++i) tot_r += rc[i];
+        if (tot_s != (int64_t)halo_send.n || tot_r != (int64_t)halo_recv.n) {
+            err = "peer counts do not add up to the halo lists"; return FVDBM_ERR_ARG;
+        }
+        send_peers.assign(sp, sp + ns); send_counts.assign(sc, sc + ns);
+        recv_peers.assign(rp, rp + nr); recv_counts.assign(rc, rc + nr);
+        CU_TRY(sendbuf.alloc((size_t)std::max<int64_t>(tot_s, 1) * Q));
+        CU_TRY(recvbuf.alloc((size_t)std::max<int64_t>(tot_r, 1) * Q));
+        drop_graphs();
         return FVDBM_OK;
     }
 
@@ -389,7 +502,8 @@ struct EngineT final : Engine {
 
     int64_t launches_per_step() const {
         if (mode == FVDBM_MODE_STAGED) return 3 + (plan.NA > 0 ? 1 : 0);
-        return (plan.NA > 0 ? 1 : 0) + (plan.Bstart > 0 ? 1 : 0) + (owned_end() > plan.Bstart ? 1 : 0);
+        return (plan.NA > 0 ? 1 : 0) + (plan.Bstart > 0 ? 1 : 0) + (owned_end() > plan.Bstart ? 1 : 0) +
+               (native_exchange() ? 3 : 0);
     }
 
     int step_timed(int n, float* ms) override {
@@ -704,6 +818,18 @@ int fvdbm_halo_set_lists(fvdbm_handle* h, const int32_t* s, int64_t ns, const in
 int fvdbm_halo_pack(fvdbm_handle* h, void* buf) { return h ? h->e->halo_pack(buf) : FVDBM_ERR_ARG; }
 int fvdbm_halo_unpack(fvdbm_handle* h, const void* buf) { return h ? h->e->halo_unpack(buf) : FVDBM_ERR_ARG; }
 void* fvdbm_stream(fvdbm_handle* h) { return h ? h->e->stream_handle() : nullptr; }
+int fvdbm_comm_unique_id(void* id_out) {
+    if (!id_out) { g_create_error = "null argument"; return FVDBM_ERR_ARG; }
+    if (!g_nccl.load()) { g_create_error = g_nccl.error; return FVDBM_ERR_CUDA; }
+    ncclUniqueId uid;
+    if (g_nccl.GetUniqueId(&uid) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return FVDBM_ERR_CUDA; }
+    memcpy(id_out, &uid, sizeof(uid));
+    return FVDBM_OK;
+}
+int fvdbm_comm_init(fvdbm_handle* h, int nranks, int rank, const void* id) { return h ? h->e->comm_init(nranks, rank, id) : FVDBM_ERR_ARG; }
+int fvdbm_halo_set_peers(fvdbm_handle* h, const int32_t* sp, const int64_t* sc, int ns, const int32_t* rp, const int64_t* rc, int nr) {
+    return h ? h->e->halo_set_peers(sp, sc, ns, rp, rc, nr) : FVDBM_ERR_ARG;
+}
 
 // ---- host-only planning -------------------------------------------------------------------------
 int fvdbm_plan_create(const fvdbm_desc* desc, fvdbm_plan** out) {

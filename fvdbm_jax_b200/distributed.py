@@ -200,7 +200,7 @@ class DistributedEnvironment:
     """torch.distributed (NCCL) driver: one process per GPU, neighbour send/recv per iteration."""
 
     def __init__(self, local: LocalMesh, dynamics, scheme: str, dtype, device: int, n_global: int,
-                 faces_per_cell: float = 1.5):
+                 faces_per_cell: float = 1.5, native: bool = True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -212,13 +212,25 @@ class DistributedEnvironment:
         self.env = self.engine.env
         self.n_owned, self.n_global, self.faces_per_cell = local.n_owned, n_global, faces_per_cell
         self.stream = torch.cuda.ExternalStream(self.env.stream_ptr, device=torch.device("cuda", device))
+        self.native = native
+        if native:
+            # torch.distributed is only the plumbing: rank 0 mints the NCCL id, everybody gets it,
+            # the engine then owns its communicator and exchanges halos without host code per step
+            ids = [None]
+            if self.rank == 0:
+                import ctypes as C
+                buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+                _lib.check(_lib.load().fvdbm_comm_unique_id(buf))
+                ids = [bytes(buf.raw)]
+            dist.broadcast_object_list(ids, src=0)
+            self.env.comm_attach(self.world, self.rank, ids[0], e.peers_send, e.send_counts, e.peers_recv, e.recv_counts)
 
     @classmethod
-    def weak_scaling_square(cls, nx, scheme, dtype, rank, world, device, reorder="hilbert"):
+    def weak_scaling_square(cls, nx, scheme, dtype, rank, world, device, reorder="hilbert", native=True):
         from .dynamics import D2Q9
         dyn = D2Q9(tau=0.8, delta_t=0.1)
         local, fpc = strip_local_mesh(nx, nx, rank, world, dyn, scheme)
-        return cls(local, dyn, scheme, dtype, device, n_global=2 * nx * nx * world, faces_per_cell=fpc)
+        return cls(local, dyn, scheme, dtype, device, n_global=2 * nx * nx * world, faces_per_cell=fpc, native=native)
 
     # ---- stepping ---------------------------------------------------------------------------------
     def _iterate(self):
@@ -233,12 +245,17 @@ class DistributedEnvironment:
         e.env.step_phase(1)
 
     def step(self, n: int = 1):
+        if self.native:
+            self.env.step(n)
+            return self
         with self.torch.cuda.stream(self.stream):
             for _ in range(n):
                 self._iterate()
         return self
 
     def step_timed(self, n: int) -> float:
+        if self.native:
+            return self.env.step_timed(n)
         torch = self.torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self.stream):

@@ -286,6 +286,18 @@ class Environment:
     def halo_unpack(self, dev_ptr: int):
         _lib.check(self._lib.fvdbm_halo_unpack(self._handle, C.c_void_p(dev_ptr)), self._handle)
 
+    def comm_attach(self, nranks: int, rank: int, unique_id: bytes, peers_send, send_counts, peers_recv, recv_counts):
+        """Native exchange: give the engine its own NCCL communicator and the per-peer layout of the
+        halo lists; afterwards ``step(n)`` runs complete distributed iterations inside the library."""
+        self.build()
+        buf = C.create_string_buffer(bytes(unique_id), _lib.COMM_ID_BYTES)
+        _lib.check(self._lib.fvdbm_comm_init(self._handle, int(nranks), int(rank), buf), self._handle)
+        sp = np.ascontiguousarray(peers_send, dtype=np.int32); sc = np.ascontiguousarray(send_counts, dtype=np.int64)
+        rp = np.ascontiguousarray(peers_recv, dtype=np.int32); rc = np.ascontiguousarray(recv_counts, dtype=np.int64)
+        _lib.check(self._lib.fvdbm_halo_set_peers(self._handle, sp.ctypes.data, sc.ctypes.data, sp.size,
+                                                  rp.ctypes.data, rc.ctypes.data, rp.size), self._handle)
+        return self
+
     def step_phase(self, phase: int):
         """phase 0: interior cells (no halo / boundary dependence); phase 1: node kernel + border
         cells + buffer swap (completes the step)."""

@@ -167,6 +167,18 @@ int  fvdbm_step_phase(fvdbm_handle* h, int phase);
 /* raw stream handle (cudaStream_t) so the host can order its collectives against the engine */
 void* fvdbm_stream(fvdbm_handle* h);
 
+/* ---- native exchange: the engine owns an NCCL communicator and runs the whole distributed
+ * iteration inside fvdbm_step (pack -> ncclSend/ncclRecv with the neighbour ranks, overlapped with
+ * the interior update -> unpack -> node kernel -> border cells), no host code per iteration.
+ * The 128-byte id comes from fvdbm_comm_unique_id on one rank and is distributed by the host
+ * (torch.distributed / MPI / a file).  libnccl.so.2 is loaded with dlopen on first use. */
+#define FVDBM_COMM_ID_BYTES 128
+int  fvdbm_comm_unique_id(void* id_out);
+int  fvdbm_comm_init(fvdbm_handle* h, int nranks, int rank, const void* id);
+/* peers and per-peer cell counts of the lists given to fvdbm_halo_set_lists (same order) */
+int  fvdbm_halo_set_peers(fvdbm_handle* h, const int32_t* send_peers, const int64_t* send_counts, int n_send_peers,
+                          const int32_t* recv_peers, const int64_t* recv_counts, int n_recv_peers);
+
 /* ---- host-only planning (no GPU needed): builds the device layout from a desc so that the
  * layout logic is unit-testable on CPU.  key = name of a plan array, see csrc/plan.hpp. */
 typedef struct fvdbm_plan fvdbm_plan;
