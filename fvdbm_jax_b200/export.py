@@ -1,0 +1,43 @@
+"""Legacy-VTK export without pyvista (reference Mesher.to_vtk, /root/reference/src/mesher.py:562-598).
+
+Writes an ASCII "# vtk DataFile Version 3.0" UNSTRUCTURED_GRID with the same cell data the
+reference attaches: ``Velocity`` (3-vector, z = 0), ``Density`` and optionally ``pdf`` / ``feq``.
+Any VTK reader (ParaView, pyvista.read) opens it."""
+from __future__ import annotations
+
+import numpy as np
+
+VTK_TRIANGLE, VTK_QUAD = 5, 9
+
+
+def write_vtk(mesher, env, filename: str, save_f: bool = False, save_feq: bool = False) -> str:
+    pts = np.asarray(mesher.points, dtype=np.float64)
+    cells = np.asarray(mesher.cells, dtype=np.int64)
+    n, k = cells.shape
+    vel = np.asarray(env.cells.vel, dtype=np.float64).reshape(n, -1)
+    rho = np.asarray(env.cells.rho, dtype=np.float64).reshape(n)
+    path = f"{filename}.vtk"
+    with open(path, "w") as f:
+        f.write("# vtk DataFile Version 3.0\nfvdbm_jax_b200 export\nASCII\nDATASET UNSTRUCTURED_GRID\n")
+        f.write(f"POINTS {pts.shape[0]} double\n")
+        np.savetxt(f, np.hstack([pts, np.zeros((pts.shape[0], 1))]), fmt="%.17g")
+        f.write(f"CELLS {n} {n * (k + 1)}\n")
+        np.savetxt(f, np.hstack([np.full((n, 1), k, dtype=np.int64), cells]), fmt="%d")
+        f.write(f"CELL_TYPES {n}\n")
+        np.savetxt(f, np.full(n, VTK_TRIANGLE if k == 3 else VTK_QUAD, dtype=np.int64), fmt="%d")
+        f.write(f"CELL_DATA {n}\n")
+        f.write("VECTORS Velocity double\n")
+        np.savetxt(f, np.hstack([vel[:, :2], np.zeros((n, 1))]), fmt="%.9g")
+        f.write("SCALARS Density double 1\nLOOKUP_TABLE default\n")
+        np.savetxt(f, rho, fmt="%.9g")
+        extra = []
+        if save_f:
+            extra.append(("pdf", np.asarray(env.cells.pdf, dtype=np.float64)))
+        if save_feq:
+            extra.append(("feq", np.asarray(env.cells.pdf_eq, dtype=np.float64)))
+        if extra:
+            f.write(f"FIELD FieldData {len(extra)}\n")
+            for name, arr in extra:
+                f.write(f"{name} {arr.shape[1]} {n} double\n")
+                np.savetxt(f, arr, fmt="%.9g")
+    return path

@@ -228,3 +228,64 @@ def strip_window(nx: int, ny_total: int, row0: int, row1: int, jitter: float = 0
     m.cell_row = np.repeat(J + row0, 2)
     m.point_gid = vid.reshape(-1)
     return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# the hand-built structured cavity of tests/ldcFVDBM.ipynb (K = 4 quads), vectorised
+# ---------------------------------------------------------------------------------------------------
+def quad_cavity(nx: int, ny: int, dynamics, u_lid: float, flux_scheme: str = "upwind"):
+    """Containers (cells, faces, nodes) of the lid-driven cavity exactly as tests/ldcFVDBM.ipynb
+    c4-c9 builds them with Environment.create + CustomArray.add_items: unit quads, faces numbered
+    vertical-first, cell faces [W, S, E, N] with signs [-1,-1,+1,+1], ghosts in stencil slot 0
+    (west/south walls) and slot 1 (east/north walls), all boundary nodes type 1, the lid is the
+    row y=0 with vel (u_lid, 0) except its two corners."""
+    from .containers import Cells, Faces, Nodes
+    N, F, P = nx * ny, nx * (ny + 1) + (nx + 1) * ny, (nx + 1) * (ny + 1)
+    cell = np.arange(N).reshape(ny, nx)
+    node = np.arange(P).reshape(ny + 1, nx + 1)
+    vert = np.arange(ny * (nx + 1)).reshape(ny, nx + 1)
+    horz = (ny * (nx + 1) + np.arange((ny + 1) * nx)).reshape(ny + 1, nx)
+    cells, faces, nodes = Cells(N, dynamics), Faces(F, dynamics, flux_scheme=flux_scheme), Nodes(P, dynamics)
+    Y, X = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    cells.face_indices = np.stack([vert[Y, X], horz[Y, X], vert[Y, X + 1], horz[Y + 1, X]], axis=-1).reshape(N, 4).astype(np.int32)
+    cells.face_normals = np.tile(np.array([-1, -1, 1, 1], dtype=np.int32), (N, 1))
+    cells.centers = np.stack([X.reshape(-1) + 0.5, Y.reshape(-1) + 0.5], axis=1)
+    # faces
+    st = -np.ones((F, 2), dtype=np.int32)
+    ni = np.zeros((F, 2), dtype=np.int32)
+    n = np.zeros((F, 2))
+    yv, xv = np.meshgrid(np.arange(ny), np.arange(nx + 1), indexing="ij")
+    fv = vert[yv, xv].reshape(-1)
+    st[fv, 0] = np.where(xv > 0, cell[yv, np.maximum(xv - 1, 0)], -1).reshape(-1)
+    st[fv, 1] = np.where(xv < nx, cell[yv, np.minimum(xv, nx - 1)], -1).reshape(-1)
+    ni[fv, 0], ni[fv, 1] = node[yv, xv].reshape(-1), node[yv + 1, xv].reshape(-1)
+    n[fv] = (1.0, 0.0)
+    yh, xh = np.meshgrid(np.arange(ny + 1), np.arange(nx), indexing="ij")
+    fh = horz[yh, xh].reshape(-1)
+    st[fh, 0] = np.where(yh > 0, cell[np.maximum(yh - 1, 0), xh], -1).reshape(-1)
+    st[fh, 1] = np.where(yh < ny, cell[np.minimum(yh, ny - 1), xh], -1).reshape(-1)
+    ni[fh, 0], ni[fh, 1] = node[yh, xh].reshape(-1), node[yh, xh + 1].reshape(-1)
+    n[fh] = (0.0, 1.0)
+    faces.stencil_cells_index, faces.nodes_index, faces.n = st, ni, n
+    faces.stencil_dists = np.full((F, 2), 0.5)
+    faces.L = np.ones((F, 1))
+    # nodes: ring order (y-1,x-1), (y-1,x), (y,x), (y,x-1), missing ones dropped, padded with -1
+    yn, xn = np.meshgrid(np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    ring = -np.ones((P, 4), dtype=np.int32)
+    dist = -np.ones((P, 4))
+    fill = np.zeros(P, dtype=np.int64)
+    for dy, dx in ((-1, -1), (-1, 0), (0, 0), (0, -1)):
+        yy, xx = (yn + dy).reshape(-1), (xn + dx).reshape(-1)
+        ok = (yy >= 0) & (yy < ny) & (xx >= 0) & (xx < nx)
+        p = np.nonzero(ok)[0]
+        ring[p, fill[p]] = cell[yy[p], xx[p]]
+        dist[p, fill[p]] = np.sqrt(2.0)
+        fill[p] += 1
+    boundary = ((yn == 0) | (yn == ny) | (xn == 0) | (xn == nx)).reshape(-1)
+    lid = ((yn == 0) & (xn > 0) & (xn < nx)).reshape(-1)
+    nodes.cells_index, nodes.cell_dists = ring, dist
+    nodes.type = boundary.astype(np.int32).reshape(P, 1)
+    vel = np.zeros((P, 2))
+    vel[lid, 0] = u_lid
+    nodes.vel = vel
+    return cells, faces, nodes

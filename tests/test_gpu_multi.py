@@ -77,3 +77,59 @@ def test_strip_windows_equal_whole_mesh():
     np.testing.assert_array_equal(got, ref)
     cl.close()
     single.close()
+
+
+def _native_worker(rank, world, port, q):
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # plumbing only; data path = engine NCCL
+    try:
+        import fvdbm_jax_b200 as fb
+        from fvdbm_jax_b200.distributed import DistributedEnvironment, strip_local_mesh
+        dyn = fb.D2Q9(0.8, 0.1)
+        nx, nyr = 40, 24
+        local, fpc = strip_local_mesh(nx, nyr, rank, world, dyn, "lax_wendroff")
+        denv = DistributedEnvironment(local, dyn, "lax_wendroff", np.float32, rank, 2 * nx * nyr * world, fpc, native=True)
+        denv.step(20)
+        pdf = np.array(denv.env.cells.pdf[:local.n_owned])
+        q.put((rank, local.cell_gid[:local.n_owned].copy(), pdf))
+        denv.close()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_native_nccl_exchange_equals_single_handle():
+    """Real multi-GPU path (engine-owned NCCL communicator, one process per GPU) == one handle."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    nx, nyr = 40, 24
+    raw = meshgen.strip_window(nx, nyr * world, 0, nyr * world)
+    _, cells, faces, nodes = global_problem(raw, "lax_wendroff", nx=nx, ny=nyr * world)
+    single = fb.Environment(cells, faces, nodes, dtype=np.float32, reorder="hilbert")
+    single.init()
+    ref = single.step(20).cells.pdf
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import os
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_native_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = np.zeros_like(ref)
+    for _ in procs:
+        rank, gid, pdf = q.get(timeout=500)
+        got[gid] = pdf
+    for p in procs:
+        p.join(timeout=120)
+    np.testing.assert_array_equal(got, ref)
+    single.close()

@@ -1,0 +1,197 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the host planner's layout (fvdbm_plan_*), Mesher parity against the reference Mesher's
+arrays (recorded in the golden fixtures), the drop-in surface, and export."""
+import ctypes as C
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+
+import golden
+import fvdbm_jax_b200 as fb
+from fvdbm_jax_b200 import _lib, meshgen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fvdbm_b200.h")).read()
+    declared = set(re.findall(r"\b(fvdbm_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/fvdbm_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert _lib.load().fvdbm_abi_version() == 1
+
+
+def test_desc_struct_matches_header_layout():
+    """ctypes mirror of fvdbm_desc: field order/size must follow the header."""
+    hdr = open(os.path.join(ROOT, "include", "fvdbm_b200.h")).read()
+    body = hdr[hdr.index("typedef struct fvdbm_desc {"):hdr.index("} fvdbm_desc;")]
+    names = re.findall(r"(?:int32_t|int64_t|double|const int32_t\*|const void\*)\s+([^;]+);", body)
+    flat = []
+    for n in names:
+        flat += [x.strip().split("[")[0].lstrip("*") for x in n.split(",")]
+    assert flat == [f[0] for f in _lib.Desc._fields_]
+    assert C.sizeof(_lib.Desc) == 8 * 4 + 4 * 8 + 2 * 8 + 16 * 8 + 4 * 8 + 15 * 8
+
+
+@pytest.mark.parametrize("name", ["cylinder_lw", "quad_ldc_d2q13", "channel_upwind"])
+def test_host_plan_layout(name):
+    case = golden.Case(name)
+    n = case.static["cells.face_indices"].shape[0]
+    perm = np.random.default_rng(1).permutation(n).astype(np.int32)
+    da = case.desc_arrays(np.float64, perm=perm)
+    hp = _lib.HostPlan(da)
+    N, K, Npad = hp.scalar("N"), da.K, hp.scalar("Npad")
+    assert hp.scalar("fused_ok") == 1 and Npad % 512 == 0
+    pos, ipos, code = hp.array("pos"), hp.array("ipos"), hp.array("ccode")
+    assert sorted(pos.tolist()) == sorted(set(pos.tolist())) and pos.min() >= 0 and pos.max() < Npad
+    assert np.array_equal(ipos[pos], np.arange(N))
+    code = code.reshape(Npad // 32, K, 32)
+    st, fi, sg = case.static["faces.stencil_cells_index"], case.static["cells.face_indices"], case.static["cells.face_normals"]
+    nb_sides = 0
+    Bstart = hp.scalar("Bstart")
+    for c in range(N):
+        p = pos[c]
+        boundary = False
+        for k in range(K):
+            cd = int(code[p >> 5, k, p & 31])
+            a, b = st[fi[c, k]]
+            other = b if a == c else a
+            if cd >= 0:
+                assert ipos[cd >> 2] == other and (cd & 1) == (0 if a == c else 1) and ((cd >> 1) & 1) == (sg[c, k] < 0)
+            else:
+                assert other == -1
+                boundary = True
+                nb_sides += 1
+        assert (p >= Bstart) == boundary            # interior cells first, border cells after Bstart
+    assert nb_sides == hp.scalar("NB")
+    holes = np.nonzero(ipos < 0)[0]
+    assert np.all(code[holes >> 5, 0, holes & 31] == np.iinfo(np.int32).min)
+    # tracked nodes: every typed node and every node of a ghost face, active ones first
+    typ = case.static["nodes.type"].reshape(-1)
+    ghost_faces = (st < 0).any(axis=1)
+    want = set(np.nonzero(typ != 0)[0].tolist()) | set(case.static["faces.nodes_index"][ghost_faces].reshape(-1).tolist())
+    tn = hp.array("tn_orig")
+    assert set(tn.tolist()) == want and hp.scalar("NT") == len(want)
+    na = hp.scalar("NA")
+    assert np.all(typ[tn[:na]] != 0) and np.all(typ[tn[na:]] == 0)
+    hp.close()
+
+
+def test_plan_rejects_bad_input():
+    case = golden.Case("ldc_tri_lw")
+    da = case.desc_arrays(np.float32)
+    bad = da.keep["cell_face_idx"].copy()
+    bad[0, 0] = -1
+    da.keep["cell_face_idx"] = bad
+    da.desc.cell_face_idx = bad.ctypes.data
+    with pytest.raises(ValueError, match="ragged"):
+        _lib.HostPlan(da)
+    da = case.desc_arrays(np.float32, perm=np.zeros(96, np.int32))
+    with pytest.raises(ValueError, match="bijection"):
+        _lib.HostPlan(da)
+    with pytest.raises(ValueError, match="Unknown flux scheme"):
+        case.scheme = "weno"
+        case.desc_arrays(np.float32)
+
+
+def test_inconsistent_mesh_falls_back_to_staged_plan():
+    case = golden.Case("ldc_tri_lw")
+    da = case.desc_arrays(np.float32)
+    bad = da.keep["cell_face_sign"].copy()
+    bad[3, 1] = 2                                     # not +-1 -> only the general staged kernels apply
+    da.keep["cell_face_sign"] = bad
+    da.desc.cell_face_sign = bad.ctypes.data
+    hp = _lib.HostPlan(da)
+    assert hp.scalar("fused_ok") == 0
+    hp.close()
+
+
+@pytest.mark.parametrize("name", [n for n in golden.names() if not n.startswith("quad")])
+def test_mesher_matches_reference_mesher(name):
+    """Integer connectivity bit-identical, float geometry to a few ulp (mesher.py docstring)."""
+    case = golden.Case(name)
+    g = case.g
+    m = fb.Mesher()
+    m.import_meshpy(case.raw())
+    m.calc_mesh_properties()
+    for key in [k[7:] for k in g.files if k.startswith("mesher.")]:
+        ref, mine = g["mesher." + key], np.asarray(getattr(m, key))
+        if ref.dtype.kind in "iu":
+            assert np.array_equal(ref, mine), key
+        else:
+            assert np.max(np.abs(ref - mine)) <= 4 * np.finfo(np.float64).eps * max(1.0, np.max(np.abs(ref))), key
+    # to_env + BC setters reproduce the statics the reference handed to Environment
+    dyn = fb.D2Q9(case.tau, case.delta_t) if case.Q == 9 else fb.D2Q13(case.tau, case.delta_t)
+    cells, faces, nodes = m.to_env(dyn, flux_method=case.scheme, dim_multiplier=float(g["meta.dim_multiplier"]))
+    for kind, marker, val in eval(str(g["meta.bcs"])):
+        nodes = m.set_vel_node(nodes, marker, np.array(val)) if kind == "vel" else m.set_rho_node(nodes, marker, val)
+    got = {"cells.face_indices": cells.face_indices, "cells.face_normals": cells.face_normals,
+           "faces.nodes_index": faces.nodes_index, "faces.stencil_cells_index": faces.stencil_cells_index,
+           "faces.stencil_dists": faces.stencil_dists, "faces.n": faces.n, "faces.L": faces.L, "nodes.type": nodes.type,
+           "nodes.cells_index": nodes.cells_index, "nodes.cell_dists": nodes.cell_dists}
+    for key, val in got.items():
+        ref = case.static[key]
+        if ref.dtype.kind in "iu":
+            assert np.array_equal(ref, np.asarray(val).reshape(ref.shape)), key
+        else:
+            assert np.allclose(ref, np.asarray(val).reshape(ref.shape), rtol=1e-15, atol=1e-16), key
+    assert np.allclose(case.init["nodes.vel"], nodes.vel) and np.allclose(case.init["nodes.rho"], nodes.rho)
+
+
+def test_quad_cavity_builder_equals_notebook_route():
+    """meshgen.quad_cavity == tests/ldcFVDBM.ipynb c4-c9 executed through the reference API."""
+    for name in ("quad_ldc_d2q9", "quad_ldc_d2q13"):
+        case = golden.Case(name)
+        dyn = (fb.D2Q9 if case.Q == 9 else fb.D2Q13)(case.tau, case.delta_t)
+        c, f, n = meshgen.quad_cavity(6, 6, dyn, 0.1)
+        for arr, key in ((c.face_indices, "cells.face_indices"), (c.face_normals, "cells.face_normals"),
+                         (f.nodes_index, "faces.nodes_index"), (f.stencil_cells_index, "faces.stencil_cells_index"),
+                         (f.stencil_dists, "faces.stencil_dists"), (f.n, "faces.n"), (f.L, "faces.L"),
+                         (n.type, "nodes.type"), (n.cells_index, "nodes.cells_index"), (n.cell_dists, "nodes.cell_dists")):
+            ref = case.static[key]
+            assert np.array_equal(np.asarray(arr, dtype=np.float64).reshape(ref.shape), ref.astype(np.float64)), key
+        assert np.array_equal(n.vel, case.init["nodes.vel"])
+
+
+def test_environment_surface_without_gpu(tmp_path):
+    """Constructor / factories / init / attribute pass-through work without touching the GPU."""
+    case = golden.Case("channel_lw")
+    cells, faces, nodes = case.containers()
+    env = fb.Environment(cells, faces, nodes)
+    env.init()
+    assert env.cells.pdf.shape == (100, 9) and env.nodes.type.shape[1] == 1 and env.faces.flux_scheme == "lax_wendroff"
+    env.cells.pdf = env.cells.pdf * 1.0                      # assignable before the engine exists
+    assert "Environment(cells=" in repr(env)
+    fb.Environment.dynamics = fb.D2Q9(0.8, 0.1)
+    e2 = fb.Environment.create(4, 6, 5)
+    e2.cells.face_indices.add_items(0, [1, 2, 3])
+    e2.init()
+    assert np.asarray(e2.cells.face_indices).shape == (4, 3) and e2.cells.face_indices[0, 2] == 3
+    e3 = fb.Environment.define(cells, faces, nodes)
+    assert e3.cells.rho.shape == (100, 1)
+    # describe() builds the C descriptor (no device needed) with dtype-cast statics
+    da = env._describe()
+    assert da.desc.N == 100 and da.desc.Q == 9 and da.desc.K == 3 and da.desc.dtype == 32
+    assert da.keep["face_n"].dtype == np.float32
+    # VTK export of host-side state
+    m = fb.Mesher()
+    m.import_meshpy(case.raw())
+    m.calc_mesh_properties()
+    path = m.to_vtk(env, str(tmp_path / "out"), save_f=True)
+    txt = open(path).read()
+    assert "UNSTRUCTURED_GRID" in txt and "VECTORS Velocity double" in txt and f"CELLS 100 400" in txt and "pdf 9 100 double" in txt
+
+
+def test_custom_array_semantics():
+    a = fb.CustomArray(3, dtype=np.int32, default_value=-1)
+    a.add_items(1, [5, 6])
+    a.add_item(1, 7)
+    a.add_item(0, 9)
+    assert np.array_equal(np.asarray(a), [[9, -1, -1], [5, 6, 7], [-1, -1, -1]])
+    assert a.shape() == (3, 3) and a[1][2] == 7
