@@ -135,7 +135,9 @@ struct EngineT final : Engine {
 
     DevBuf<real> pdf[2];
     DevBuf<int32_t> ccode, bf_na, bf_nb, pos, ipos, ring_off, ring_cell, tn_type;
-    DevBuf<real> ccoef, bf_ratio, ring_w, npdf, nrho, nvel;
+    DevBuf<real> ccoef, fcoef, bf_ratio, ring_w, npdf, nrho, nvel;
+    DevBuf<int32_t> cface;
+    int layout = 1;                      // 0: per-side coefficients, 1: shared face records (fewer bytes)
     DevBuf<int32_t> s_cface, s_csign, s_fcell, s_fnode;
     DevBuf<real> s_fdist, s_fn, s_fL;
     DevBuf<real> s_rho, s_ux, s_uy, s_feq, s_flux;     // staged dynamics (lazy)
@@ -206,8 +208,10 @@ struct EngineT final : Engine {
         CU_TRY(pos.upload(plan.pos, stream));
         CU_TRY(ipos.upload(plan.ipos, stream));
         if (plan.fused_ok) {
+            if (const char* e = getenv("FVDBM_COEF_LAYOUT")) layout = atoi(e) ? 1 : 0;
             CU_TRY(ccode.upload(plan.ccode, stream));
-            CU_TRY(ccoef.upload(plan.ccoef, stream));
+            if (layout == 0) CU_TRY(ccoef.upload(plan.ccoef, stream));
+            else { CU_TRY(cface.upload(plan.cface, stream)); CU_TRY(fcoef.upload(plan.fcoef, stream)); }
             CU_TRY(bf_na.upload(plan.bf_na, stream));
             CU_TRY(bf_nb.upload(plan.bf_nb, stream));
             CU_TRY(bf_ratio.upload(plan.bf_ratio, stream));
@@ -228,12 +232,14 @@ struct EngineT final : Engine {
         CU_TRY(s_fL.upload(static_cast<const real*>(d.face_L), (size_t)plan.F, stream));
         CU_TRY(cudaStreamSynchronize(stream));
         // host staging vectors are no longer needed
-        plan.ccode = {}; plan.ccoef = {}; plan.s_cface = {}; plan.s_csign = {}; plan.s_fcell = {}; plan.s_fnode = {};
+        plan.ccode = {}; plan.ccoef = {}; plan.cface = {}; plan.fcoef = {}; plan.s_cface = {}; plan.s_csign = {}; plan.s_fcell = {}; plan.s_fnode = {};
         plan.ring_cell = {}; plan.ring_w = {}; plan.tn_pdf = {};
         int rc = set(FVDBM_CELL_PDF, d.cell_pdf, (size_t)plan.N * Q * sizeof(real));
         if (rc) return rc;
         // opt-in shared memory for the TMA kernel
-        CU_TRY(cudaFuncSetAttribute(k_fused_tma<real, Q, K, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU_TRY(cudaFuncSetAttribute(k_fused_tma<real, Q, K, SCHEME, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)prop.sharedMemPerBlockOptin));
+        CU_TRY(cudaFuncSetAttribute(k_fused_tma<real, Q, K, SCHEME, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)prop.sharedMemPerBlockOptin));
         max_smem = prop.sharedMemPerBlockOptin;
         if (const char* e = getenv("FVDBM_VARIANT")) variant = atoi(e);
@@ -248,12 +254,16 @@ struct EngineT final : Engine {
     size_t max_smem = 0;
     int occ_cache = 0;
 
+    size_t stage_bytes(int tc) const {
+        return layout == 0 ? tma_stage_bytes<real, Q, K, SCHEME, 0>(tc) : tma_stage_bytes<real, Q, K, SCHEME, 1>(tc);
+    }
+
     int sanitize_options() {
         if (variant != FVDBM_VARIANT_DIRECT && variant != FVDBM_VARIANT_TMA) { err = "unknown variant"; return FVDBM_ERR_ARG; }
         if (tile_cells != 128 && tile_cells != 256 && tile_cells != 512) { err = "tile_cells must be 128, 256 or 512"; return FVDBM_ERR_ARG; }
         if (stages < 2 || stages > 8) { err = "stages must be in 2..8"; return FVDBM_ERR_ARG; }
-        while (stages > 2 && kTmaHeader + stages * tma_stage_bytes<real, Q, K, SCHEME>(tile_cells) > max_smem) --stages;
-        while (tile_cells > 128 && kTmaHeader + stages * tma_stage_bytes<real, Q, K, SCHEME>(tile_cells) > max_smem) tile_cells /= 2;
+        while (stages > 2 && kTmaHeader + stages * stage_bytes(tile_cells) > max_smem) --stages;
+        while (tile_cells > 128 && kTmaHeader + stages * stage_bytes(tile_cells) > max_smem) tile_cells /= 2;
         if (graph_steps < 0) graph_steps = 0;
         if (graph_steps & 1) ++graph_steps;
         return FVDBM_OK;
@@ -264,7 +274,7 @@ struct EngineT final : Engine {
         FusedArgs<real> a;
         a.P = P;
         a.pdf_in = pdf[cur].p; a.pdf_out = pdf[cur ^ 1].p;
-        a.ccode = ccode.p; a.ccoef = ccoef.p;
+        a.ccode = ccode.p; a.ccoef = ccoef.p; a.cface = cface.p; a.fcoef = fcoef.p;
         a.G.bf_na = bf_na.p; a.G.bf_nb = bf_nb.p; a.G.bf_ratio = bf_ratio.p;
         a.G.npdf = npdf.p; a.G.NTpad = plan.NTpad;
         a.cell_begin = begin; a.cell_end = end;
@@ -288,13 +298,15 @@ struct EngineT final : Engine {
         if (end <= begin) return FVDBM_OK;
         FusedArgs<real> a = fused_args(begin, end);
         if (variant == FVDBM_VARIANT_DIRECT) {
-            k_fused_direct<real, Q, K, SCHEME><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
+            if (layout == 0) k_fused_direct<real, Q, K, SCHEME, 0><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
+            else k_fused_direct<real, Q, K, SCHEME, 1><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
         } else {
-            const size_t smem = kTmaHeader + (size_t)stages * tma_stage_bytes<real, Q, K, SCHEME>(tile_cells);
+            const size_t smem = kTmaHeader + (size_t)stages * stage_bytes(tile_cells);
             int per_sm = ctas_per_sm;
             if (per_sm <= 0) {
                 if (occ_cache <= 0) {
-                    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_fused_tma<real, Q, K, SCHEME>, tile_cells, smem));
+                    if (layout == 0) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_fused_tma<real, Q, K, SCHEME, 0>, tile_cells, smem));
+                    else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_fused_tma<real, Q, K, SCHEME, 1>, tile_cells, smem));
                     if (occ_cache < 1) occ_cache = 1;
                 }
                 per_sm = occ_cache;
@@ -302,7 +314,8 @@ struct EngineT final : Engine {
             const int64_t ntiles = (end - begin) / tile_cells;
             int64_t grid = (int64_t)num_sms * per_sm;
             if (grid > ntiles) grid = ntiles;
-            k_fused_tma<real, Q, K, SCHEME><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
+            if (layout == 0) k_fused_tma<real, Q, K, SCHEME, 0><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
+            else k_fused_tma<real, Q, K, SCHEME, 1><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
         }
         ++launches;
         CU_TRY(cudaGetLastError());
@@ -673,7 +686,7 @@ struct EngineT final : Engine {
         case FVDBM_INFO_TRACKED_NODES: *v = plan.NT; break;
         case FVDBM_INFO_BOUNDARY_SIDES: *v = plan.NB; break;
         case FVDBM_INFO_DEVICE_BYTES:
-            *v = (int64_t)(pdf[0].bytes() * 2 + ccode.bytes() + ccoef.bytes() + s_cface.bytes() * 2 + s_fcell.bytes() * 2 +
+            *v = (int64_t)(pdf[0].bytes() * 2 + ccode.bytes() + ccoef.bytes() + cface.bytes() + fcoef.bytes() + s_cface.bytes() * 2 + s_fcell.bytes() * 2 +
                            s_fdist.bytes() * 2 + s_fL.bytes() + pos.bytes() + ipos.bytes() + s_flux.bytes() + s_feq.bytes() +
                            scratch.bytes());
             break;
@@ -760,9 +773,9 @@ template <typename real>
 int64_t plan_array(const Plan<real>& p, const std::string& k, const void** ptr, int32_t* eb) {
 #define I32(name) if (k == #name) { *ptr = p.name.data(); *eb = 4; return (int64_t)p.name.size(); }
 #define REAL(name) if (k == #name) { *ptr = p.name.data(); *eb = (int32_t)sizeof(real); return (int64_t)p.name.size(); }
-    I32(pos) I32(ipos) I32(ccode) I32(bf_na) I32(bf_nb) I32(tn_orig) I32(tn_type) I32(node_track)
+    I32(pos) I32(ipos) I32(ccode) I32(cface) I32(bf_na) I32(bf_nb) I32(tn_orig) I32(tn_type) I32(node_track)
     I32(ring_off) I32(ring_cell) I32(s_cface) I32(s_csign) I32(s_fcell) I32(s_fnode)
-    REAL(ccoef) REAL(bf_ratio) REAL(ring_w) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel)
+    REAL(ccoef) REAL(fcoef) REAL(bf_ratio) REAL(ring_w) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel)
 #undef I32
 #undef REAL
     return -1;
@@ -772,7 +785,7 @@ int64_t plan_scalar(const Plan<real>& p, const std::string& k) {
     if (k == "N") return p.N; if (k == "F") return p.F; if (k == "P") return p.P; if (k == "No") return p.No;
     if (k == "Npad") return p.Npad; if (k == "Bstart") return p.Bstart; if (k == "Oend") return p.Oend;
     if (k == "Hstart") return p.Hstart; if (k == "NB") return p.NB; if (k == "NT") return p.NT;
-    if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "NC") return p.NC;
+    if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "NF") return p.NF; if (k == "NC") return p.NC;
     if (k == "fused_ok") return p.fused_ok ? 1 : 0;
     return -1;
 }

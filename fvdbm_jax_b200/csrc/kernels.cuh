@@ -17,19 +17,39 @@ struct FusedArgs {
     const real* __restrict__ pdf_in;
     real* __restrict__ pdf_out;
     const int32_t* __restrict__ ccode;
-    const real* __restrict__ ccoef;
+    const real* __restrict__ ccoef;    // cell layout (LAYOUT 0): per-side coefficients, tiled like the codes
+    const int32_t* __restrict__ cface; // face layout (LAYOUT 1): side -> record index
+    const real* __restrict__ fcoef;    //                          records [NF][NC], one per face
     GhostTables<real> G;               // boundary sides + tracked node populations
     int64_t cell_begin, cell_end;      // position range, multiples of the CTA tile
     int reverse;                       // 1: sweep tiles from the top (L2 reuse of last step's writes)
 };
 
-template <typename real>
-__device__ __forceinline__ real ldg_stream(const real* p) { return __ldg(p); }
+// one face record (NC coefficients, NC*sizeof(real) bytes, naturally aligned) with the widest loads
+template <typename real, int NC>
+__device__ __forceinline__ void load_face_record(const real* __restrict__ base, int32_t rec, real* out);
+template <> __device__ __forceinline__ void load_face_record<float, 4>(const float* __restrict__ base, int32_t rec, float* out) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base) + rec);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <> __device__ __forceinline__ void load_face_record<float, 2>(const float* __restrict__ base, int32_t rec, float* out) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(base) + rec);
+    out[0] = v.x; out[1] = v.y;
+}
+template <> __device__ __forceinline__ void load_face_record<double, 4>(const double* __restrict__ base, int32_t rec, double* out) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(base) + 2 * (size_t)rec);
+    const double2 b = __ldg(reinterpret_cast<const double2*>(base) + 2 * (size_t)rec + 1);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+}
+template <> __device__ __forceinline__ void load_face_record<double, 2>(const double* __restrict__ base, int32_t rec, double* out) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(base) + rec);
+    out[0] = a.x; out[1] = a.y;
+}
 
 // ------------------------------------------------------------------------------------------------
 // V1: thread per cell, everything through L1/L2.
 // ------------------------------------------------------------------------------------------------
-template <typename real, int Q, int K, int SCHEME>
+template <typename real, int Q, int K, int SCHEME, int LAYOUT>
 __global__ void __launch_bounds__(256) k_fused_direct(const FusedArgs<real> a) {
     constexpr int NC = SCHEME == 0 ? 2 : 4;
     const int64_t nblk = gridDim.x;
@@ -44,10 +64,16 @@ __global__ void __launch_bounds__(256) k_fused_direct(const FusedArgs<real> a) {
     if (code[0] == kHole) return;
 #pragma unroll
     for (int k = 1; k < K; ++k) code[k] = __ldg(gc + k * kTW);
-    const real* gco = a.ccoef + tile * (K * NC * kTW) + lane;
     real coef[K * NC];
+    if (LAYOUT == 0) {
+        const real* gco = a.ccoef + tile * (K * NC * kTW) + lane;
 #pragma unroll
-    for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
+        for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
+    } else {
+        const int32_t* gf = a.cface + tile * (K * kTW) + lane;
+#pragma unroll
+        for (int k = 0; k < K; ++k) load_face_record<real, NC>(a.fcoef, __ldg(gf + k * kTW), coef + k * NC);
+    }
     const real* gp = a.pdf_in + tile * (Q * kTW) + lane;
     real f[Q], out[Q];
 #pragma unroll
@@ -97,12 +123,13 @@ __device__ __forceinline__ void fence_barrier_init() {
 
 constexpr int kTmaHeader = 128;   // bytes reserved for the mbarriers in front of the stage ring
 
-template <typename real, int Q, int K, int SCHEME>
+template <typename real, int Q, int K, int SCHEME, int LAYOUT>
 __host__ __device__ constexpr size_t tma_stage_bytes(int tile_cells) {
-    return (size_t)tile_cells * ((Q + K * (SCHEME == 0 ? 2 : 4)) * sizeof(real) + K * sizeof(int32_t));
+    return LAYOUT == 0 ? (size_t)tile_cells * ((Q + K * (SCHEME == 0 ? 2 : 4)) * sizeof(real) + K * sizeof(int32_t))
+                       : (size_t)tile_cells * (Q * sizeof(real) + 2 * K * sizeof(int32_t));
 }
 
-template <typename real, int Q, int K, int SCHEME>
+template <typename real, int Q, int K, int SCHEME, int LAYOUT>
 __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, const int stages) {
     constexpr int NC = SCHEME == 0 ? 2 : 4;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -110,7 +137,8 @@ __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, cons
     const int tid = threadIdx.x;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     const size_t pdf_bytes = (size_t)TC * Q * sizeof(real);
-    const size_t coef_bytes = (size_t)TC * K * NC * sizeof(real);
+    // second region of a stage: per-side coefficients (cell layout) or per-side record ids (face layout)
+    const size_t coef_bytes = LAYOUT == 0 ? (size_t)TC * K * NC * sizeof(real) : (size_t)TC * K * sizeof(int32_t);
     const size_t code_bytes = (size_t)TC * K * sizeof(int32_t);
     const size_t stage_bytes = pdf_bytes + coef_bytes + code_bytes;
     unsigned char* ring = smem + kTmaHeader;
@@ -127,7 +155,8 @@ __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, cons
         const size_t mt = (size_t)(base >> 5);
         mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
         bulk_g2s(st, a.pdf_in + mt * (Q * kTW), (uint32_t)pdf_bytes, &full[s]);
-        bulk_g2s(st + pdf_bytes, a.ccoef + mt * (K * NC * kTW), (uint32_t)coef_bytes, &full[s]);
+        if (LAYOUT == 0) bulk_g2s(st + pdf_bytes, a.ccoef + mt * (K * NC * kTW), (uint32_t)coef_bytes, &full[s]);
+        else bulk_g2s(st + pdf_bytes, a.cface + mt * (K * kTW), (uint32_t)coef_bytes, &full[s]);
         bulk_g2s(st + pdf_bytes + coef_bytes, a.ccode + mt * (K * kTW), (uint32_t)code_bytes, &full[s]);
     };
 
@@ -153,6 +182,7 @@ __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, cons
         unsigned char* st = ring + (size_t)s * stage_bytes;
         const real* s_pdf = reinterpret_cast<const real*>(st);
         const real* s_coef = reinterpret_cast<const real*>(st + pdf_bytes) + (size_t)mt_local * (K * NC * kTW) + lane;
+        const int32_t* s_face = reinterpret_cast<const int32_t*>(st + pdf_bytes) + (size_t)mt_local * (K * kTW) + lane;
         const int32_t* s_code = reinterpret_cast<const int32_t*>(st + pdf_bytes + coef_bytes) + (size_t)mt_local * (K * kTW) + lane;
         int32_t code[K];
         code[0] = s_code[0];
@@ -160,8 +190,13 @@ __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, cons
 #pragma unroll
             for (int k = 1; k < K; ++k) code[k] = s_code[k * kTW];
             real coef[K * NC];
+            if (LAYOUT == 0) {
 #pragma unroll
-            for (int i = 0; i < K * NC; ++i) coef[i] = s_coef[i * kTW];
+                for (int i = 0; i < K * NC; ++i) coef[i] = s_coef[i * kTW];
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) load_face_record<real, NC>(a.fcoef, s_face[k * kTW], coef + k * NC);
+            }
             const real* sp = s_pdf + (size_t)mt_local * (Q * kTW) + lane;
             real f[Q], out[Q];
 #pragma unroll

@@ -43,8 +43,9 @@ struct Plan {
     std::vector<int32_t> pos, ipos;
     bool fused_ok = true;
     std::string why_not;
-    std::vector<int32_t> ccode;
-    std::vector<real> ccoef;
+    std::vector<int32_t> ccode, cface;          // side codes; side -> shared face record (face layout)
+    std::vector<real> ccoef, fcoef;             // per-side coefficients (cell layout) / per-face records [NF][NC]
+    int64_t NF = 0;                             // face records referenced by owned cells
     int64_t NB = 0;
     std::vector<int32_t> bf_na, bf_nb;
     std::vector<real> bf_ratio;
@@ -221,8 +222,18 @@ struct Plan {
             ccoef.assign((size_t)ntile * K * NC * TW, real(0));
             for (int64_t q = 0; q < Npad; ++q)
                 if (ipos[q] < 0 || ipos[q] >= No) ccode[(size_t)(q >> 5) * K * TW + (q & 31)] = HOLE;
-            for (int64_t c = 0; c < No; ++c) {
-                const int64_t pc = pos[c], tile = pc >> 5, lane = pc & 31;
+            // two interchangeable coefficient layouts:
+            //   cell layout: ccoef[tile][k*NC+i][lane]   (perfectly coalesced, interior faces stored twice)
+            //   face layout: fcoef[rec][NC] + cface[tile][k][lane] -> rec (one 16 B record per face, shared by
+            //                both cells; records numbered by first touch in position order for locality)
+            cface.assign((size_t)ntile * K * TW, 0);
+            std::vector<int32_t> rec_of(F, -1);
+            fcoef.clear();
+            NF = 0;
+            for (int64_t pc = 0; pc < Npad; ++pc) {
+                const int64_t c = ipos[pc];
+                if (c < 0 || c >= No) continue;
+                const int64_t tile = pc >> 5, lane = pc & 31;
                 for (int k = 0; k < K; ++k) {
                     const int64_t j = d.cell_face_idx[c * K + k];
                     const int sl = slot[c * K + k];
@@ -239,15 +250,21 @@ struct Plan {
                         ++NB;
                     }
                     ccode[(size_t)(tile * K + k) * TW + lane] = code;
-                    real* co = &ccoef[(size_t)(tile * K + k) * NC * TW + lane];
+                    real co[4] = {0, 0, 0, 0};
                     const real L = fL[j];
-                    co[0 * TW] = fn[2 * j] * L;
-                    co[1 * TW] = fn[2 * j + 1] * L;
+                    co[0] = fn[2 * j] * L;
+                    co[1] = fn[2 * j + 1] * L;
                     if (NC == 4) {
                         const real d0 = fdist[2 * j], d1 = fdist[2 * j + 1], dd = d0 + d1;
-                        co[2 * TW] = d0 / dd;
-                        co[3 * TW] = real(1) / (real(2) * dd * L);
+                        co[2] = d0 / dd;
+                        co[3] = real(1) / (real(2) * dd * L);
                     }
+                    for (int i = 0; i < NC; ++i) ccoef[(size_t)((tile * K + k) * NC + i) * TW + lane] = co[i];
+                    if (rec_of[j] < 0) {
+                        rec_of[j] = (int32_t)NF++;
+                        for (int i = 0; i < NC; ++i) fcoef.push_back(co[i]);
+                    }
+                    cface[(size_t)(tile * K + k) * TW + lane] = rec_of[j];
                 }
             }
             if (NB >= (int64_t(1) << 28)) return fail("too many boundary sides");

@@ -142,7 +142,7 @@ def cylinder_channel(scale: int = 1, seed: int = 0) -> RawMesh:
 def porous_channel(scale: int = 1, seed: int = 0, n_obst: int = 60) -> RawMesh:
     """Porous-flow-like domain (tests/porous_flow.ipynb geometry: box (-93,0)-(279,186) with 60
     obstacles); obstacles here are deterministic pseudo-random discs since the outline blob
-    (tests/test_bmp.mat) need not travel.  ``scale=4`` ~ 2M cells (config 3)."""
+    (tests/test_bmp.mat) need not travel.  ``scale=4`` ~ 0.5M cells, ``scale=8`` ~ 2M cells (config 3)."""
     lx, ly = 372.0, 186.0
     nx, ny = 186 * scale, 93 * scale
     rng = np.random.default_rng(1234 + seed)

@@ -5,6 +5,7 @@
 // the way k_nodes + k_fused_direct do on the GPU.  tests/test_hostsim.py compares it with the
 // oracle, so layout/encoding/arithmetic mistakes are caught in the GPU-less build container.
 // This file is NOT part of libfvdbm_b200.so and no product path can reach it.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,7 +62,14 @@ static int run(const fvdbm_desc& d, int nsteps, void* o_pdf, void* o_npdf, void*
             code[0] = pl.ccode[tile * (K * kTW) + lane];
             if (code[0] == kHole) continue;
             for (int k = 1; k < K; ++k) code[k] = pl.ccode[tile * (K * kTW) + k * kTW + lane];
-            for (int i = 0; i < K * NC; ++i) coef[i] = pl.ccoef[tile * (K * NC * kTW) + i * kTW + lane];
+            if (getenv("HOSTSIM_COEF_LAYOUT") && atoi(getenv("HOSTSIM_COEF_LAYOUT")) == 0) {
+                for (int i = 0; i < K * NC; ++i) coef[i] = pl.ccoef[tile * (K * NC * kTW) + i * kTW + lane];
+            } else {          // face layout: shared record per face
+                for (int k = 0; k < K; ++k) {
+                    const int32_t rec = pl.cface[tile * (K * kTW) + k * kTW + lane];
+                    for (int i = 0; i < NC; ++i) coef[k * NC + i] = pl.fcoef[(size_t)rec * NC + i];
+                }
+            }
             for (int q = 0; q < Q; ++q) f[q] = pin[tile * (Q * kTW) + q * kTW + lane];
             auto load_nbr = [pin](int64_t nb, real* fn) {
                 for (int q = 1; q < Q; ++q) fn[q] = pin[pdf_index<Q>(nb) + q * kTW];

@@ -8,6 +8,11 @@ import fvdbm_jax_b200 as fb  # noqa: E402
 from fvdbm_jax_b200 import _lib, meshgen  # noqa: E402
 
 
+def quad_ldc():
+    dyn = fb.D2Q13(tau=0.8, delta_t=0.1)
+    return "ldc_quads_100x100_d2q13", meshgen.quad_cavity(100, 100, dyn, 0.1)
+
+
 def problems():
     dyn = fb.D2Q9(tau=0.8, delta_t=0.1)
     raw = meshgen.triangulated_square(100, 100, seed=0)
@@ -16,7 +21,7 @@ def problems():
     cyl = [("vel", 4, [0.1, 0]), ("vel", 3, [0, 0]), ("vel", 1, [0, 0]), ("vel", 5, [0, 0]), ("rho", 2, 0.95)]
     yield "cylinder_scale9", meshgen.cylinder_channel(scale=9), dyn2, "lax_wendroff", cyl
     por = [("vel", 5, [0, 0]), ("vel", 1, [0, 0]), ("vel", 3, [0, 0]), ("rho", 4, 1.05), ("rho", 2, 0.95)]
-    yield "porous_scale4", meshgen.porous_channel(scale=4), dyn2, "lax_wendroff", por
+    yield "porous_scale8", meshgen.porous_channel(scale=8), dyn2, "lax_wendroff", por
 
 
 def main():
@@ -24,12 +29,18 @@ def main():
     ap.add_argument("--graphs", default="0,10,50")
     ap.add_argument("--steps", type=int, default=2000)
     args = ap.parse_args()
-    for name, raw, dyn, scheme, bcs in problems():
-        m = fb.Mesher(); m.import_meshpy(raw); m.calc_mesh_properties()
-        cells, faces, nodes = m.to_env(dyn, flux_method=scheme)
-        for kind, mk, val in bcs:
-            nodes = m.set_vel_node(nodes, mk, np.array(val, dtype=float)) if kind == "vel" else m.set_rho_node(nodes, mk, val)
-        n = cells.face_indices.shape[0]
+    def built():
+        name, (cells, faces, nodes) = quad_ldc()
+        yield name, cells, faces, nodes
+        for name, raw, dyn, scheme, bcs in problems():
+            m = fb.Mesher(); m.import_meshpy(raw); m.calc_mesh_properties()
+            cells, faces, nodes = m.to_env(dyn, flux_method=scheme)
+            for kind, mk, val in bcs:
+                nodes = m.set_vel_node(nodes, mk, np.array(val, dtype=float)) if kind == "vel" else m.set_rho_node(nodes, mk, val)
+            yield name, cells, faces, nodes
+
+    for name, cells, faces, nodes in built():
+        n = np.asarray(cells.face_indices).shape[0]
         env = fb.Environment(cells, faces, nodes, dtype=np.float32)
         env.init(); env.build()
         for g in [int(x) for x in args.graphs.split(",")]:
