@@ -137,7 +137,8 @@ struct EngineT final : Engine {
     DevBuf<int32_t> ccode, bf_na, bf_nb, pos, ipos, ring_off, ring_cell, tn_type;
     DevBuf<real> ccoef, fcoef, bf_ratio, ring_w, npdf, nrho, nvel;
     DevBuf<int32_t> cface;
-    int layout = 1;                      // 0: per-side coefficients, 1: shared face records (fewer bytes)
+    int layout = 0;                      // 0: per-side coefficients (default, coalesced); 1: shared face records
+                                         // (12 B/cell fewer, but measured 7% slower: 16 B gathers)
     DevBuf<int32_t> s_cface, s_csign, s_fcell, s_fnode;
     DevBuf<real> s_fdist, s_fn, s_fL;
     DevBuf<real> s_rho, s_ux, s_uy, s_feq, s_flux;     // staged dynamics (lazy)

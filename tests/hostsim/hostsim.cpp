@@ -62,7 +62,7 @@ static int run(const fvdbm_desc& d, int nsteps, void* o_pdf, void* o_npdf, void*
             code[0] = pl.ccode[tile * (K * kTW) + lane];
             if (code[0] == kHole) continue;
             for (int k = 1; k < K; ++k) code[k] = pl.ccode[tile * (K * kTW) + k * kTW + lane];
-            if (getenv("HOSTSIM_COEF_LAYOUT") && atoi(getenv("HOSTSIM_COEF_LAYOUT")) == 0) {
+            if (!(getenv("HOSTSIM_COEF_LAYOUT") && atoi(getenv("HOSTSIM_COEF_LAYOUT")) == 1)) {
                 for (int i = 0; i < K * NC; ++i) coef[i] = pl.ccoef[tile * (K * NC * kTW) + i * kTW + lane];
             } else {          // face layout: shared record per face
                 for (int k = 0; k < K; ++k) {
