@@ -154,8 +154,11 @@ def run_reference(args):
 
 
 def workload_config(args, nx, cells, inner):
-    return {"workload": f"synthetic triangulated square nx=ny={nx} ({'%d cells' % cells if cells else '2*nx*ny cells'}), "
-                        f"x-periodic + y walls (lid 0.1), D2Q9 tau=0.8 dt=0.1, {args.scheme}, per-GPU under weak scaling",
+    if getattr(args, "scaling", "weak") == "strong" and args.impl == "b200":
+        shape = f"fixed global mesh nx={nx} x ny={args.ny_total} quads ({2 * nx * args.ny_total} cells) cut into one strip per GPU"
+    else:
+        shape = f"nx=ny={nx} ({'%d cells' % cells if cells else '2*nx*ny cells'}) per GPU (weak scaling: strips of one global square)"
+    return {"workload": f"synthetic triangulated square, {shape}, x-periodic + y walls (lid 0.1), D2Q9 tau=0.8 dt=0.1, {args.scheme}",
             "inner_iterations_per_step": inner, "scheme": args.scheme, "l2": "inputs exceed L2 (no flush needed)",
             "reorder": args.reorder, "variant": args.variant, "tile_cells": args.tile, "stages": args.stages,
             "reverse_sweep": args.reverse, "graph_steps": args.graph}
@@ -182,6 +185,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-nx", type=int, default=1000)
     ap.add_argument("--ref-inner", type=int, default=10)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: nx x nx quads per GPU (default); strong: a fixed nx x ny_total global mesh split into strips")
+    ap.add_argument("--ny-total", type=int, default=8944, help="strong scaling: quad rows of the global mesh")
     ap.add_argument("--torch-exchange", action="store_true",
                     help="N>1: drive the halo exchange from Python with torch.distributed P2P instead of the engine's own NCCL communicator")
     args = ap.parse_args()
@@ -204,12 +210,26 @@ def main():
     torch.cuda.set_device(local)
     real = np.float32 if args.dtype == "f32" else np.float64
 
+    if args.scaling == "strong" and args.ny_total % world:
+        raise SystemExit("--ny-total must be divisible by the number of GPUs")
     if world > 1:
         from fvdbm_jax_b200.distributed import DistributedEnvironment
-        denv = DistributedEnvironment.weak_scaling_square(args.nx, args.scheme, real, rank, world, local,
-                                                          reorder=args.reorder, native=not args.torch_exchange)
+        rows = args.nx if args.scaling == "weak" else args.ny_total // world
+        denv = DistributedEnvironment.strips(args.nx, rows, args.scheme, real, rank, world, local,
+                                             native=not args.torch_exchange)
         env, n_local, n_global = denv, denv.n_owned, denv.n_global
         stepper = denv
+    elif args.scaling == "strong":
+        # same mesh family as the multi-GPU strips (hash jitter), whole mesh on one GPU
+        from fvdbm_jax_b200.distributed import strip_local_mesh, containers_from_mesh
+        dyn = fb.D2Q9(tau=0.8, delta_t=0.1)
+        lm, fpc_strong = strip_local_mesh(args.nx, args.ny_total, 0, 1, dyn, args.scheme)
+        cells, faces, nodes = containers_from_mesh(lm.mesh, dyn, args.scheme)
+        env = fb.Environment(cells, faces, nodes, dtype=real, device=local, reorder=args.reorder)
+        env.init()
+        env.build()
+        n_local = n_global = lm.n_owned
+        stepper = env
     else:
         m, dyn, cells, faces, nodes, t_mesh = build_problem(args.nx, args.nx, args.scheme)
         env = fb.Environment(cells, faces, nodes, dtype=real, device=local, reorder=args.reorder)
@@ -314,7 +334,7 @@ def main():
         except Exception:
             pass
     line = {"metric": "MCUPS", "value": value, "unit": "MCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, args.nx, n_local, inner), "roofline": roofline,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfvdbm_b200.so")
+LIB_PATH = os.environ.get("FVDBM_LIB", os.path.join(HERE, "libfvdbm_b200.so"))   # FVDBM_LIB: A/B builds
 
 ABI_VERSION = 1
 COMM_ID_BYTES = 128

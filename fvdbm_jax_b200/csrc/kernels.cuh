@@ -25,6 +25,36 @@ struct FusedArgs {
     int reverse;                       // 1: sweep tiles from the top (L2 reuse of last step's writes)
 };
 
+// ---- build-time tuning knobs (A/B'd on B200, see profiles/) -----------------------------------
+#ifndef FVDBM_DIRECT_MINCTAS
+#define FVDBM_DIRECT_MINCTAS 0        // >0: __launch_bounds__(256, N) for the direct kernel
+#endif
+#ifndef FVDBM_STREAM_HINTS
+#define FVDBM_STREAM_HINTS 0          // 1: ld.global.cs for the never-reused side records, st.global.cs for stores
+#endif
+#if FVDBM_DIRECT_MINCTAS > 0
+#define FVDBM_DIRECT_BOUNDS __launch_bounds__(256, FVDBM_DIRECT_MINCTAS)
+#else
+#define FVDBM_DIRECT_BOUNDS __launch_bounds__(256)
+#endif
+
+template <typename T>
+__device__ __forceinline__ T ld_static(const T* p) {     // side codes / coefficients: streamed once per step
+#if FVDBM_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void st_result(T* p, T v) {   // new populations: not re-read during this step
+#if FVDBM_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // one face record (NC coefficients, NC*sizeof(real) bytes, naturally aligned) with the widest loads
 template <typename real, int NC>
 __device__ __forceinline__ void load_face_record(const real* __restrict__ base, int32_t rec, real* out);
@@ -50,7 +80,7 @@ template <> __device__ __forceinline__ void load_face_record<double, 2>(const do
 // V1: thread per cell, everything through L1/L2.
 // ------------------------------------------------------------------------------------------------
 template <typename real, int Q, int K, int SCHEME, int LAYOUT>
-__global__ void __launch_bounds__(256) k_fused_direct(const FusedArgs<real> a) {
+__global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     constexpr int NC = SCHEME == 0 ? 2 : 4;
     const int64_t nblk = gridDim.x;
     const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
@@ -60,19 +90,19 @@ __global__ void __launch_bounds__(256) k_fused_direct(const FusedArgs<real> a) {
     const int lane = (int)(c & 31);
     const int32_t* gc = a.ccode + tile * (K * kTW) + lane;
     int32_t code[K];
-    code[0] = __ldg(gc);
+    code[0] = ld_static(gc);
     if (code[0] == kHole) return;
 #pragma unroll
-    for (int k = 1; k < K; ++k) code[k] = __ldg(gc + k * kTW);
+    for (int k = 1; k < K; ++k) code[k] = ld_static(gc + k * kTW);
     real coef[K * NC];
     if (LAYOUT == 0) {
         const real* gco = a.ccoef + tile * (K * NC * kTW) + lane;
 #pragma unroll
-        for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
+        for (int i = 0; i < K * NC; ++i) coef[i] = ld_static(gco + i * kTW);
     } else {
         const int32_t* gf = a.cface + tile * (K * kTW) + lane;
 #pragma unroll
-        for (int k = 0; k < K; ++k) load_face_record<real, NC>(a.fcoef, __ldg(gf + k * kTW), coef + k * NC);
+        for (int k = 0; k < K; ++k) load_face_record<real, NC>(a.fcoef, ld_static(gf + k * kTW), coef + k * NC);
     }
     const real* gp = a.pdf_in + tile * (Q * kTW) + lane;
     real f[Q], out[Q];
@@ -87,7 +117,7 @@ __global__ void __launch_bounds__(256) k_fused_direct(const FusedArgs<real> a) {
     advance_cell<real, Q, K, SCHEME>(a.P, a.G, f, code, coef, load_nbr, out);
     real* go = a.pdf_out + tile * (Q * kTW) + lane;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) go[q * kTW] = out[q];
+    for (int q = 0; q < Q; ++q) st_result(go + q * kTW, out[q]);
 }
 
 // ------------------------------------------------------------------------------------------------

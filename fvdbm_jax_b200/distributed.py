@@ -227,10 +227,17 @@ class DistributedEnvironment:
 
     @classmethod
     def weak_scaling_square(cls, nx, scheme, dtype, rank, world, device, reorder="hilbert", native=True):
+        """nx x nx quads per rank: the global mesh grows with the number of GPUs."""
+        return cls.strips(nx, nx, scheme, dtype, rank, world, device, native=native)
+
+    @classmethod
+    def strips(cls, nx, ny_per_rank, scheme, dtype, rank, world, device, native=True):
+        """Global nx x (ny_per_rank*world) x-periodic square, one horizontal strip per rank."""
         from .dynamics import D2Q9
         dyn = D2Q9(tau=0.8, delta_t=0.1)
-        local, fpc = strip_local_mesh(nx, nx, rank, world, dyn, scheme)
-        return cls(local, dyn, scheme, dtype, device, n_global=2 * nx * nx * world, faces_per_cell=fpc, native=native)
+        local, fpc = strip_local_mesh(nx, ny_per_rank, rank, world, dyn, scheme)
+        return cls(local, dyn, scheme, dtype, device, n_global=2 * nx * ny_per_rank * world, faces_per_cell=fpc,
+                   native=native)
 
     # ---- stepping ---------------------------------------------------------------------------------
     def _iterate(self):
