@@ -32,10 +32,13 @@ struct FusedArgs {
 #ifndef FVDBM_STREAM_HINTS
 #define FVDBM_STREAM_HINTS 0          // 1: ld.global.cs for the never-reused side records, st.global.cs for stores
 #endif
+// measured on B200 (profiles/r1_experiment_occupancy_cachehints.txt): fp32 is best left to ptxas
+// (48 regs, 5 CTAs/SM; forcing 6 or 8 CTAs spills and loses 2-18 %), fp64 gains 15 % from 3 CTAs/SM
+// (96 -> 80 regs: 0.492 -> 0.426 ms at 10M cells).
 #if FVDBM_DIRECT_MINCTAS > 0
 #define FVDBM_DIRECT_BOUNDS __launch_bounds__(256, FVDBM_DIRECT_MINCTAS)
 #else
-#define FVDBM_DIRECT_BOUNDS __launch_bounds__(256)
+#define FVDBM_DIRECT_BOUNDS __launch_bounds__(256, (sizeof(real) == 8 ? 3 : 1))
 #endif
 
 template <typename T>
