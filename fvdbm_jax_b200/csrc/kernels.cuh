@@ -38,7 +38,7 @@ struct FusedArgs {
 #if FVDBM_DIRECT_MINCTAS > 0
 #define FVDBM_DIRECT_BOUNDS __launch_bounds__(256, FVDBM_DIRECT_MINCTAS)
 #else
-#define FVDBM_DIRECT_BOUNDS __launch_bounds__(256, (sizeof(real) == 8 ? 3 : 1))
+#define FVDBM_DIRECT_BOUNDS __launch_bounds__(256, (sizeof(real) == 8 ? 3 : (Q == 9 ? 5 : 4)))
 #endif
 
 template <typename T>
