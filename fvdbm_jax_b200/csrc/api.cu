@@ -492,7 +492,7 @@ struct EngineT final : Engine {
         int rc;
         if (mode == FVDBM_MODE_STAGED && (rc = ensure_staged_buffers())) return rc;
         while (n > 0) {
-            if (graph_steps > 0 && n >= graph_steps && !phase0_done) {
+            if (graph_steps > 0 && n >= graph_steps && !phase0_done && !native_exchange()) {   // NCCL ops stay out of graphs
                 auto it = graphs.find(cur);
                 if (it == graphs.end()) {
                     cudaGraphExec_t ge;

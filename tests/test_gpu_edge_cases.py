@@ -1,0 +1,131 @@
+"""Edge cases of the hot path on the GPU, each against the NumPy oracle."""
+import types
+
+import numpy as np
+import pytest
+
+import golden
+
+pytestmark = pytest.mark.gpu
+
+fb = pytest.importorskip("fvdbm_jax_b200")
+from fvdbm_jax_b200 import _lib, meshgen  # noqa: E402
+from oracle.step_numpy import StepOracle  # noqa: E402
+
+
+def static_state(cells, faces, nodes):
+    static = {"cells.face_indices": cells.face_indices, "cells.face_normals": cells.face_normals,
+              "faces.nodes_index": faces.nodes_index, "faces.stencil_cells_index": faces.stencil_cells_index,
+              "faces.stencil_dists": faces.stencil_dists, "faces.n": faces.n, "faces.L": faces.L,
+              "nodes.type": nodes.type, "nodes.cells_index": nodes.cells_index, "nodes.cell_dists": nodes.cell_dists}
+    state = {"cells.pdf": cells.pdf, "nodes.pdf": nodes.pdf, "nodes.rho": nodes.rho, "nodes.vel": nodes.vel}
+    return static, state
+
+
+def compare(env, oracle, tol, names=golden.STATE):
+    exp = oracle.state()
+    for name in names:
+        obj, attr = name.split(".")
+        err = golden.rel_err(getattr(getattr(env, obj), attr), exp[name])
+        assert err < tol, f"{name}: {err:.3e}"
+
+
+def mesh_problem(raw, scheme="lax_wendroff", bcs=(("vel", 1, (0.0, 0.0)), ("vel", 3, (0.1, 0.0)))):
+    m = fb.Mesher()
+    m.import_meshpy(raw)
+    m.calc_mesh_properties()
+    dyn = fb.D2Q9(0.8, 0.1)
+    cells, faces, nodes = m.to_env(dyn, scheme)
+    for kind, mk, val in bcs:
+        nodes = m.set_vel_node(nodes, mk, np.array(val)) if kind == "vel" else m.set_rho_node(nodes, mk, val)
+    return m, dyn, cells, faces, nodes
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (2, 1), (3, 2)])
+@pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_TMA])
+def test_tiny_meshes(nx, ny, variant):
+    """2-12 cells: far fewer cells than one 32-lane tile, every cell on the boundary."""
+    m, dyn, cells, faces, nodes = mesh_problem(meshgen.triangulated_square(nx, ny, jitter=0.0),
+                                               bcs=(("vel", 1, (0, 0)), ("vel", 2, (0, 0)), ("vel", 4, (0, 0)), ("vel", 3, (0.1, 0))))
+    static, state = static_state(cells, faces, nodes)
+    o = StepOracle(static, state, 9, dyn.tau, dyn.delta_t, "lax_wendroff", np.float64).step(7)
+    env = fb.Environment(cells, faces, nodes, dtype=np.float64)
+    env.init()
+    env.set_option(_lib.OPT_VARIANT, variant)
+    compare(env.step(7), o, 1e-11)
+    env.close()
+
+
+def fan_mesh(n_tri=40):
+    """Half-disc fan: boundary node 0 is shared by n_tri (> 32) triangles -> ring wider than a warp."""
+    ang = np.linspace(0.0, np.pi, n_tri + 1)
+    pts = np.concatenate([[[0.0, 0.0]], np.stack([np.cos(ang), np.sin(ang)], axis=1)])
+    el = np.stack([np.zeros(n_tri, int), 1 + np.arange(n_tri), 2 + np.arange(n_tri)], axis=1).astype(np.int32)
+    markers = np.full(pts.shape[0], 2, dtype=np.int32)       # arc nodes
+    markers[[0, 1, n_tri + 1]] = 1                            # the flat side incl. the hub
+    return types.SimpleNamespace(points=pts, elements=el, faces=meshgen.unique_edges(el, pts.shape[0]), point_markers=markers)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 1e-5)])
+def test_ring_wider_than_a_warp(dtype, tol):
+    m, dyn, cells, faces, nodes = mesh_problem(fan_mesh(40), bcs=(("vel", 1, (0.05, 0.0)), ("rho", 2, 0.98)))
+    assert nodes.cells_index.shape[1] == 40
+    static, state = static_state(cells, faces, nodes)
+    o = StepOracle(static, state, 9, dyn.tau, dyn.delta_t, "lax_wendroff", dtype).step(15)
+    for mode in ("fused", "staged"):
+        env = fb.Environment(cells, faces, nodes, dtype=dtype, mode=mode)
+        env.init()
+        compare(env.step(15), o, tol)
+        env.close()
+
+
+def test_general_signs_use_the_staged_kernels():
+    """cells.face_normals need not be +-1 in the reference (any int multiplies the flux,
+    src/containers.py:119): such meshes are routed to the reference-shaped staged kernels."""
+    case = golden.Case("channel_lw")
+    cells, faces, nodes = case.containers()
+    sg = np.array(cells.face_normals, copy=True)
+    sg[::7, 1] *= 2
+    cells.face_normals = sg
+    static = dict(case.static)
+    static["cells.face_normals"] = sg
+    o = StepOracle(static, case.init, case.Q, case.tau, case.delta_t, case.scheme, np.float64).step(6)
+    env = fb.Environment(cells, faces, nodes, dtype=np.float64)
+    env.init()
+    env = env.step(6)
+    assert env.info(_lib.INFO_MODE) == _lib.MODE_STAGED and env.info(_lib.INFO_FUSED_OK) == 0
+    compare(env, o, 1e-11)
+    with pytest.raises(ValueError, match="fused mode unavailable"):
+        fb.Environment(cells, faces, nodes, mode="fused").step()
+    env.close()
+
+
+def test_boundary_values_can_change_mid_run():
+    """Re-binding nodes.vel / nodes.rho between steps (what set_vel_node does before a run)."""
+    case = golden.Case("channel_lw")
+    cells, faces, nodes = case.containers()
+    env = fb.Environment(cells, faces, nodes, dtype=np.float64)
+    env.init()
+    env = env.step(3)
+    o = case.oracle(np.float64).step(3)
+    vel = np.array(env.nodes.vel)
+    inlet = np.nonzero(np.asarray(nodes.type).reshape(-1) == 1)[0]
+    vel[inlet, 0] *= 0.5
+    env.nodes.vel = vel
+    o.nvel[inlet, 0] *= 0.5
+    compare(env.step(4), o.step(4), 1e-11)
+    env.close()
+
+
+def test_upwind_axis_aligned_faces_where_ksi_dot_n_is_zero():
+    """Unjittered mesh: many faces have KSI.n == 0 exactly -> the `>= 0` upwind tie-break matters."""
+    m, dyn, cells, faces, nodes = mesh_problem(meshgen.triangulated_square(12, 9, jitter=0.0), scheme="upwind",
+                                               bcs=(("vel", 1, (0, 0)), ("vel", 2, (0, 0)), ("vel", 4, (0, 0)), ("vel", 3, (0.1, 0))))
+    c = m.cell_centers
+    cells.pdf = dyn.calc_eq(1 + 0.02 * np.sin(c[:, 0]), 0.03 * np.stack([np.cos(c[:, 1]), np.sin(c[:, 0])], axis=1))
+    static, state = static_state(cells, faces, nodes)
+    o = StepOracle(static, state, 9, dyn.tau, dyn.delta_t, "upwind", np.float64).step(10)
+    env = fb.Environment(cells, faces, nodes, dtype=np.float64)
+    env.init()
+    compare(env.step(10), o, 1e-11)
+    env.close()

@@ -79,6 +79,77 @@ def test_strip_windows_equal_whole_mesh():
     single.close()
 
 
+def _native_general_worker(rank, world, port, q):
+    """General unstructured decomposition (obstacle mesh, Hilbert chunks + greedy refinement): every
+    rank builds the small global mesh, extracts its own part, and exchanges with several peers."""
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fvdbm_jax_b200.distributed import DistributedEnvironment
+        from fvdbm_jax_b200.partition import extract_local
+        dyn, g, part = _cylinder_global(world)
+        local = extract_local(g, part, rank)
+        denv = DistributedEnvironment(local, dyn, "lax_wendroff", np.float32, rank, g.num_cells, 1.5, native=True)
+        denv.step(30)
+        q.put((rank, local.cell_gid[:local.n_owned].copy(), np.array(denv.env.cells.pdf[:local.n_owned]),
+               len(denv.engine.peers_recv)))
+        denv.close()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _cylinder_global(world):
+    raw = meshgen.masked_domain(72, 36, 24.0, 12.0, lambda x, y: (x - 7.0) ** 2 + (y - 6.0) ** 2 < 4.0, seed=6)
+    m = fb.Mesher()
+    m.import_meshpy(raw)
+    m.calc_mesh_properties()
+    dyn = fb.D2Q9(0.65, 0.1)
+    cells, faces, nodes = m.to_env(dyn, "lax_wendroff")
+    for mk, v in ((4, (0.1, 0.0)), (3, (0.0, 0.0)), (1, (0.0, 0.0)), (5, (0.0, 0.0))):
+        nodes = m.set_vel_node(nodes, mk, np.array(v))
+    nodes = m.set_rho_node(nodes, 2, 0.95)
+    g = GlobalMesh.from_containers(cells, faces, nodes)
+    part = refine_partition(g.stencil, partition_sfc(g.centers, world), world)
+    return dyn, g, part
+
+
+@pytest.mark.timeout(600)
+def test_native_nccl_general_partition_equals_single_handle():
+    import os
+    import torch
+    import torch.multiprocessing as mp
+    from fvdbm_jax_b200.distributed import containers_from_mesh
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    dyn, g, part = _cylinder_global(world)
+    single = fb.Environment(*containers_from_mesh(g, dyn, "lax_wendroff"), dtype=np.float32, reorder="hilbert")
+    single.init()
+    ref = single.step(30).cells.pdf
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 1000
+    procs = [ctx.Process(target=_native_general_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = np.zeros_like(ref)
+    for _ in procs:
+        rank, gid, pdf, npeers = q.get(timeout=500)
+        got[gid] = pdf
+        assert npeers >= 1
+    for p in procs:
+        p.join(timeout=120)
+    np.testing.assert_array_equal(got, ref)
+    single.close()
+
+
 def _native_worker(rank, world, port, q):
     import os, sys
     import numpy as np

@@ -1,0 +1,59 @@
+"""Drop-in check with the REFERENCE's own objects (build container only, needs /root/reference):
+containers built by the reference Mesher / Environment.create under the jax shim are accepted by
+fvdbm_jax_b200.Environment and describe the same problem as our own containers."""
+import numpy as np
+import pytest
+
+import golden
+from oracle import refrun
+
+pytestmark = pytest.mark.skipif(not refrun.available(), reason="reference tree not present on this box")
+
+
+def test_reference_mesher_route_is_accepted():
+    import fvdbm_jax_b200 as fb
+    ns = refrun.load()
+    case = golden.Case("channel_lw")
+    m = refrun.ref_mesher(case.raw())
+    dyn = ns.D2Q9(tau=case.tau, delta_t=case.delta_t)
+    cells, faces, nodes = m.to_env(dyn, flux_method="lax_wendroff")
+    nodes = m.set_vel_node(nodes, 4, ns.jnp.array([0.05, 0.0]))
+    nodes = m.set_vel_node(nodes, 1, ns.jnp.array([0.0, 0.0]))
+    nodes = m.set_vel_node(nodes, 3, ns.jnp.array([0.0, 0.0]))
+    nodes = m.set_rho_node(nodes, 2, 0.95)
+    env = fb.Environment(cells, faces, nodes, dtype=np.float64)       # reference objects, jax(-shim) arrays
+    env.init()
+    da = env._describe()
+    ours = fb.Environment(*case.containers(), dtype=np.float64)._describe()
+    for key in ("cell_face_idx", "cell_face_sign", "face_cell_idx", "face_dists", "face_node_idx", "face_n", "face_L",
+                "node_type", "node_cell_idx", "node_cell_dist", "node_rho", "node_vel"):
+        assert np.array_equal(da.keep[key], ours.keep[key]), key
+    assert da.desc.Q == 9 and da.desc.K == 3 and da.desc.scheme == 1 and abs(da.desc.tau - case.tau) < 1e-15
+
+
+def test_reference_create_route_with_custom_arrays_is_accepted():
+    import fvdbm_jax_b200 as fb
+    ns = refrun.load()
+    ns.Environment.dynamics = ns.D2Q13(tau=0.8, delta_t=0.1)
+    ref_env = ns.Environment.create(2, 7, 6)                         # CustomArray-backed containers
+    ref_env.cells.face_indices.add_items(0, ns.jnp.asarray([0, 1, 2, 3]))
+    ref_env.cells.face_indices.add_items(1, ns.jnp.asarray([2, 4, 5, 6]))
+    ref_env.cells.face_normals.add_items(0, ns.jnp.asarray([0, 0, 1, 1]))   # notebook c7: 0 first, then -> -1
+    ref_env.cells.face_normals.add_items(1, ns.jnp.asarray([0, 0, 1, 1]))   # (-1 is CustomArray's "empty" marker)
+    ref_env.cells.face_normals.data = ns.jnp.where(ref_env.cells.face_normals.data == 0, -1, ref_env.cells.face_normals.data)
+    for j, st in enumerate([(-1, 0), (-1, 0), (0, 1), (0, -1), (-1, 1), (1, -1), (1, -1)]):
+        ref_env.faces.stencil_cells_index.add_items(j, ns.jnp.asarray([s if s >= 0 else -2 for s in st]))
+        ref_env.faces.stencil_dists.add_items(j, ns.jnp.asarray([.5, .5]))
+        ref_env.faces.nodes_index.add_items(j, ns.jnp.asarray([j % 6, (j + 1) % 6]))
+    ref_env.faces.stencil_cells_index.data = ns.jnp.where(ref_env.faces.stencil_cells_index.data == -2, -1,
+                                                          ref_env.faces.stencil_cells_index.data)
+    for p in range(6):
+        ref_env.nodes.cells_index.add_items(p, ns.jnp.asarray([p % 2]))
+        ref_env.nodes.cell_dists.add_items(p, ns.jnp.asarray([1.0]))
+    env = fb.Environment.define(ref_env.cells, ref_env.faces, ref_env.nodes)
+    env.init()                                                       # calls the reference containers' init()
+    da = env._describe()
+    assert da.desc.Q == 13 and da.desc.K == 4 and da.desc.N == 2 and da.desc.F == 7 and da.desc.P == 6
+    assert da.keep["face_cell_idx"].tolist()[3] == [0, -1] and da.keep["node_cell_idx"].shape == (6, 1)
+    hp = fb._lib.HostPlan(da)
+    assert hp.scalar("fused_ok") == 1 and hp.scalar("NB") == 6
