@@ -75,6 +75,7 @@ class _CellsView(_View):
 class _FacesView(_View):
     _dynamic = {"pdf": "faces.pdf"}
     _static = ("nodes_index", "stencil_cells_index", "stencil_dists", "n", "L", "flux_scheme")
+    _optional = ("alpha",)
 
 
 class _NodesView(_View):
@@ -161,6 +162,13 @@ class Environment:
         N = fi.shape[0]
         scheme = getattr(f, "flux_scheme", "upwind")
         stencil = _np(f.stencil_cells_index)
+        face_L = np.asarray(_np(f.L), dtype=real).reshape(-1)
+        if hasattr(f, "npq"):
+            raise ValueError("CCStencilKsiFaces (cc_alt_upwind) is inoperable in the reference (divides by "
+                             "KSI.n_PQ = 0 -> NaN) and is not supported")
+        if hasattr(f, "alpha"):
+            # CCStencilFaces (reference src/faces.py:54-72): flux * cos(alpha) == face length * cos(alpha)
+            face_L = (face_L * np.cos(np.asarray(_np(f.alpha), dtype=real).reshape(-1))).astype(real)
         host = self._host
         host["cells.pdf"] = np.array(_np(c.pdf), dtype=real).reshape(N, Q)
         host["cells.rho"] = np.array(_np(c.rho), dtype=real).reshape(N, 1)
@@ -178,7 +186,7 @@ class Environment:
             dtype=real, scheme=scheme, Q=Q, K=K, tau=float(dyn.tau), delta_t=float(dyn.delta_t),
             lattice_constants=_LATTICES[Q].lattice_constants(real),
             cell_face_idx=fi, cell_face_sign=_np(c.face_normals), face_cell_idx=stencil,
-            face_dists=_np(f.stencil_dists), face_node_idx=_np(f.nodes_index), face_n=_np(f.n), face_L=_np(f.L),
+            face_dists=_np(f.stencil_dists), face_node_idx=_np(f.nodes_index), face_n=_np(f.n), face_L=face_L,
             node_type=_np(n.type), node_cell_idx=_np(n.cells_index), node_cell_dist=_np(n.cell_dists),
             cell_pdf=host["cells.pdf"], node_pdf=host["nodes.pdf"], node_rho=host["nodes.rho"],
             node_vel=host["nodes.vel"], cell_perm=perm, n_owned=self._n_owned, device_id=self.device, mode=mode)
@@ -362,8 +370,8 @@ class Environment:
             pre = {"_CellsView": "cells", "_FacesView": "faces", "_NodesView": "nodes"}[type(view).__name__]
             for k in type(view)._dynamic:
                 st[f"{pre}.{k}"] = np.array(_np(getattr(view, k)))
-            for k in type(view)._static:
-                if k != "flux_scheme":
+            for k in type(view)._static + getattr(type(view), "_optional", ()):
+                if k != "flux_scheme" and hasattr(view._src, k):
                     st[f"{pre}.{k}"] = np.array(_np(getattr(view._src, k)))
         if hasattr(c, "centers"):
             st["cells.centers"] = np.array(c.centers)

@@ -178,6 +178,27 @@ class Mesher:
         dists[g1, 1] = dists[g1, 0]
         self.face_cell_center_distances = dists
 
+        # cell-centre stencil (cc_* flux methods): direction c0 -> c1 (discovery order) or cell -> face
+        # centre, aligned with the face normal (mesher.py:506-544); distances projected on it with the
+        # same slot order as above (mesher.py:231-256); angle to the face normal (mesher.py:546-558)
+        cc0 = self.cell_centers[np.maximum(c0, 0)]
+        v = np.where(interior[:, None], self.cell_centers[np.maximum(c1, 0)] - cc0, self.face_centers - cc0)
+        v = np.where((cnt > 0)[:, None], v, 0.0)
+        vn = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1])
+        sn = np.where((vn > 0)[:, None], v / np.where(vn > 0, vn, 1.0)[:, None], v)
+        fnu = fn / np.sqrt(fn[:, 0] * fn[:, 0] + fn[:, 1] * fn[:, 1])[:, None]
+        snu = sn / (np.sqrt(sn[:, 0] * sn[:, 0] + sn[:, 1] * sn[:, 1])[:, None] + 1e-14)
+        sn = np.where((_dot(fnu, snu) < 0)[:, None], -sn, sn)
+        self.stencil_norms = sn
+        q0 = np.where(cnt > 0, _dot(sn, self.cell_centers[np.maximum(c0, 0)] - hmid[he0]), -1.0)
+        q1 = np.where(cnt > 1, _dot(sn, self.cell_centers[np.maximum(c1, 0)] - hmid[he1]), -1.0)
+        cc = np.abs(np.stack([np.where(swap, q1, q0), np.where(swap, q0, q1)], axis=1))
+        cc[g0, 0] = cc[g0, 1]
+        cc[g1, 1] = cc[g1, 0]
+        self.cc_stencil_dist = cc
+        snn = sn / np.sqrt(sn[:, 0] * sn[:, 0] + sn[:, 1] * sn[:, 1])[:, None]
+        self.face_stencil_angles = np.arccos(np.clip(_dot(fnu, snn), -1.0, 1.0))
+
         # node -> ring cells (ascending), padded with -1; distances node-centroid (mesher.py:286-316)
         vpt = self._canon(cells.reshape(-1)).astype(np.int64)
         vorder = np.argsort(vpt, kind="stable")
@@ -199,20 +220,31 @@ class Mesher:
 
     # ------------------------------------------------------------------ to_env
     def to_env(self, dynamics, flux_method="upwind", dim_multiplier=1):
-        """reference mesher.py:610-693 for the operable flux methods ("upwind", "lax_wendroff")."""
-        if flux_method not in ("upwind", "lax_wendroff"):
+        """reference mesher.py:610-693: "upwind", "lax_wendroff" and the cell-centre-stencil variants
+        "cc_upwind" / "cc_lax_wendroff" (CCStencilFaces, src/faces.py:10-76: stencil direction as n,
+        stencil-projected distances, flux * cos(alpha)).  "cc_alt_upwind" (CCStencilKsiFaces) divides by
+        KSI.n_PQ, which is 0 for axis-aligned stencils, and yields NaN in the reference itself."""
+        if flux_method == "cc_alt_upwind":
+            raise ValueError("Unsupported flux method: cc_alt_upwind (inoperable in the reference: NaN)")
+        if flux_method not in ("upwind", "lax_wendroff", "cc_upwind", "cc_lax_wendroff"):
             raise ValueError(f"Unsupported flux method: {flux_method}")
+        cc = flux_method.startswith("cc_")
+        if cc and self.point_alias is not None:
+            raise ValueError("cc_* flux methods are not available on periodic meshes")
         cells = Cells(self.cells.shape[0], dynamics)
         cells.face_indices = np.asarray(self.cell_face_indices, dtype=np.int32)
         cells.face_normals = np.asarray(self.cell_face_normal_signs, dtype=np.int32)
         cells.centers = np.asarray(self.cell_centers, dtype=np.float64)   # extension: locality renumbering
 
-        faces = Faces(self.faces.shape[0], dynamics, flux_scheme=flux_method)
-        faces.n = np.asarray(self.face_normals, dtype=np.float64)
+        faces = Faces(self.faces.shape[0], dynamics, flux_scheme=flux_method[3:] if cc else flux_method)
+        if cc:
+            faces.alpha = np.asarray(self.face_stencil_angles, dtype=np.float64)[..., np.newaxis]
+        faces.n = np.asarray(self.stencil_norms if cc else self.face_normals, dtype=np.float64)
         faces.L = np.asarray(self.face_lengths, dtype=np.float64)[..., np.newaxis] * dim_multiplier
         faces.nodes_index = self._canon(np.asarray(self.faces, dtype=np.int32)).astype(np.int32)
         faces.stencil_cells_index = np.asarray(self.face_cell_indices, dtype=np.int32)
-        faces.stencil_dists = np.asarray(self.face_cell_center_distances, dtype=np.float64) * dim_multiplier
+        faces.stencil_dists = np.asarray(self.cc_stencil_dist if cc else self.face_cell_center_distances,
+                                         dtype=np.float64) * dim_multiplier
 
         nodes = Nodes(self.points.shape[0], dynamics)
         nodes.cells_index = np.asarray(self.point_cell_indices, dtype=np.int32)

@@ -128,7 +128,8 @@ def finish(name, env, rec, steps, dyn, scheme, dim_multiplier, bcs):
     rec["meta.K"] = np.int64(rec["static.cells.face_indices"].shape[1])
     rec["meta.tau"] = np.float64(dyn.tau)
     rec["meta.delta_t"] = np.float64(dyn.delta_t)
-    rec["meta.scheme"] = np.array(scheme)
+    rec["meta.scheme"] = np.array(str(env.faces.flux_scheme))        # "upwind" | "lax_wendroff" (cc_* use the same two)
+    rec["meta.flux_method"] = np.array(scheme)
     rec["meta.steps"] = np.array(sorted(steps), dtype=np.int64)
     rec["meta.float_bits"] = np.int64(ns.float_dtype.itemsize * 8)
     rec["meta.dim_multiplier"] = np.float64(dim_multiplier)
@@ -169,6 +170,8 @@ def main():
     cyl = meshgen.masked_domain(24, 12, 24.0, 12.0, lambda x, y: (x - 7.0) ** 2 + (y - 6.0) ** 2 < 4.0, seed=6)
     tri_case("cylinder_lw", cyl, "lax_wendroff", CYL, [1, 2, 5], tau=0.65)
     tri_case("tri_d2q13_lw", sq(6, 5, seed=7), "lax_wendroff", WALLS_LID, [1, 2, 5], lattice="D2Q13")
+    tri_case("cc_ldc_upwind", sq(7, 6, seed=8), "cc_upwind", WALLS_LID, [1, 2, 5, 12])
+    tri_case("cc_channel_lw", sq(9, 5, seed=9), "cc_lax_wendroff", CHANNEL, [1, 2, 5, 12], tau=0.65, dim_multiplier=1.5)
     quad_ldc_case("quad_ldc_d2q13", 6, "D2Q13", [1, 2, 5, 20])
     quad_ldc_case("quad_ldc_d2q9", 6, "D2Q9", [1, 2, 5, 20])
     quad_ldc_case("quad_ldc_d2q9_lw", 5, "D2Q9", [1, 2, 5], scheme="lax_wendroff")

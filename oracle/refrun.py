@@ -70,7 +70,7 @@ def ref_mesher(raw):
 MESHER_FIELDS = ("points", "cells", "faces", "point_markers", "cell_centers", "face_centers",
                  "face_normals", "face_lengths", "cell_face_indices", "cell_face_normal_signs",
                  "face_cell_indices", "face_cell_center_distances", "point_cell_indices",
-                 "point_cell_center_distances")
+                 "point_cell_center_distances", "stencil_norms", "cc_stencil_dist", "face_stencil_angles")
 
 
 def mesher_arrays(m) -> dict:
@@ -90,7 +90,10 @@ def _get(env, dotted):
 
 
 def snapshot(env, names=STATE) -> dict:
-    return {n: _get(env, n) for n in names}
+    out = {n: _get(env, n) for n in names}
+    if names is STATIC and hasattr(env.faces, "alpha"):            # CCStencilFaces (src/faces.py:10-76)
+        out["faces.alpha"] = _get(env, "faces.alpha")
+    return out
 
 
 def run_steps(env, checkpoints):

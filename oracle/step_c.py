@@ -47,7 +47,10 @@ class COracle:
         arr("face_dists", static["faces.stencil_dists"], real, (F, 2))
         arr("face_node_idx", static["faces.nodes_index"], np.int32, (F, 2))
         arr("face_n", static["faces.n"], real, (F, 2))
-        arr("face_L", static["faces.L"], real, (F,))
+        L = np.asarray(static["faces.L"], dtype=real).reshape(F)
+        if "faces.alpha" in static:      # CCStencilFaces: flux * cos(alpha) == a face length scaled by cos(alpha)
+            L = (L * np.cos(np.asarray(static["faces.alpha"], dtype=real).reshape(F))).astype(real)
+        arr("face_L", L, real, (F,))
         arr("node_type", static["nodes.type"], np.int32, (P,))
         arr("node_cell_idx", ring, np.int32, (P, M))
         arr("node_cell_dist", static["nodes.cell_dists"], real, (P, M))

@@ -13,6 +13,7 @@ Each stage cites the reference lines it restates (paths relative to /root/refere
   S3 boundary nodes src/environment.py:62 -> src/containers.py:339-404, utils/utils.py:34-60
   S4 face flux      src/environment.py:63 -> src/containers.py:191-287, utils/utils.py:153-154
   S5 cell update    src/environment.py:64 -> src/containers.py:107-121
+  cc stencil faces  src/faces.py:10-76 (CCStencilFaces: S4 flux times cos(alpha))
 """
 from __future__ import annotations
 
@@ -71,6 +72,8 @@ class StepOracle:
         self.dists = f(static["faces.stencil_dists"])                 # (F,2)
         self.n = f(static["faces.n"])                                 # (F,2)
         self.L = f(static["faces.L"]).reshape(-1, 1)                  # (F,1)
+        # CCStencilFaces (src/faces.py:54-72): flux * cos(alpha); absent for the base Faces
+        self.cos_alpha = np.cos(f(static["faces.alpha"]).reshape(-1, 1)) if "faces.alpha" in static else None
         self.type = i(static["nodes.type"]).reshape(-1, 1)            # (P,1)
         self.ring = i(static["nodes.cells_index"])                    # (P,M), -1 padded
         self.ring_d = f(static["nodes.cell_dists"])                   # (P,M), -1 padded
@@ -144,6 +147,8 @@ class StepOracle:
             interp = (d0[:, None] / dd) - (varpi * self.delta_t) / (2 * dd)
             fs = f0 + (f1 - f0) * interp
         self.flux = fs * varpi * self.L
+        if self.cos_alpha is not None:
+            self.flux = self.flux * self.cos_alpha
 
     def cells(self):                                                  # S5
         fl = self.flux[self.face_indices] * self.face_signs[..., None].astype(self.dtype)

@@ -56,6 +56,8 @@ class Case:
         faces = fb.Faces(s["faces.n"].shape[0], dyn, flux_scheme=self.scheme)
         faces.nodes_index, faces.stencil_cells_index = s["faces.nodes_index"], s["faces.stencil_cells_index"]
         faces.stencil_dists, faces.n, faces.L, faces.pdf = s["faces.stencil_dists"], s["faces.n"], s["faces.L"], i["faces.pdf"]
+        if "faces.alpha" in s:
+            faces.alpha = s["faces.alpha"]
         nodes = fb.Nodes(s["nodes.type"].shape[0], dyn)
         nodes.type, nodes.cells_index, nodes.cell_dists = s["nodes.type"], s["nodes.cells_index"], s["nodes.cell_dists"]
         nodes.pdf, nodes.rho, nodes.vel = i["nodes.pdf"], i["nodes.rho"], i["nodes.vel"]
@@ -65,11 +67,14 @@ class Case:
         from fvdbm_jax_b200 import _lib, D2Q9, D2Q13
         s, i = self.static, self.init
         lat = (D2Q9 if self.Q == 9 else D2Q13).lattice_constants(dtype)
+        face_L = np.asarray(s["faces.L"], dtype=dtype).reshape(-1)
+        if "faces.alpha" in s:        # same folding as Environment._describe
+            face_L = (face_L * np.cos(np.asarray(s["faces.alpha"], dtype=dtype).reshape(-1))).astype(dtype)
         return _lib.DescArrays(
             dtype=dtype, scheme=self.scheme, Q=self.Q, K=self.K, tau=self.tau, delta_t=self.delta_t,
             lattice_constants=lat, cell_face_idx=s["cells.face_indices"], cell_face_sign=s["cells.face_normals"],
             face_cell_idx=s["faces.stencil_cells_index"], face_dists=s["faces.stencil_dists"],
-            face_node_idx=s["faces.nodes_index"], face_n=s["faces.n"], face_L=s["faces.L"],
+            face_node_idx=s["faces.nodes_index"], face_n=s["faces.n"], face_L=face_L,
             node_type=s["nodes.type"], node_cell_idx=s["nodes.cells_index"], node_cell_dist=s["nodes.cell_dists"],
             cell_pdf=i["cells.pdf"], node_pdf=i["nodes.pdf"], node_rho=i["nodes.rho"], node_vel=i["nodes.vel"],
             cell_perm=perm, mode=mode)

@@ -124,11 +124,17 @@ def test_mesher_matches_reference_mesher(name):
         ref, mine = g["mesher." + key], np.asarray(getattr(m, key))
         if ref.dtype.kind in "iu":
             assert np.array_equal(ref, mine), key
+        elif key == "face_stencil_angles":            # arccos amplifies the last-bit differences near alpha = 0
+            assert np.max(np.abs(ref - mine)) <= 1e-7, key
         else:
             assert np.max(np.abs(ref - mine)) <= 4 * np.finfo(np.float64).eps * max(1.0, np.max(np.abs(ref))), key
     # to_env + BC setters reproduce the statics the reference handed to Environment
     dyn = fb.D2Q9(case.tau, case.delta_t) if case.Q == 9 else fb.D2Q13(case.tau, case.delta_t)
-    cells, faces, nodes = m.to_env(dyn, flux_method=case.scheme, dim_multiplier=float(g["meta.dim_multiplier"]))
+    method = str(g["meta.flux_method"]) if "meta.flux_method" in g.files else case.scheme
+    cells, faces, nodes = m.to_env(dyn, flux_method=method, dim_multiplier=float(g["meta.dim_multiplier"]))
+    assert faces.flux_scheme == case.scheme
+    if method.startswith("cc_"):
+        assert np.allclose(case.static["faces.alpha"], faces.alpha, rtol=0, atol=1e-7)   # arccos near 0 amplifies ulps
     for kind, marker, val in eval(str(g["meta.bcs"])):
         nodes = m.set_vel_node(nodes, marker, np.array(val)) if kind == "vel" else m.set_rho_node(nodes, marker, val)
     got = {"cells.face_indices": cells.face_indices, "cells.face_normals": cells.face_normals,
@@ -195,3 +201,20 @@ def test_custom_array_semantics():
     a.add_item(0, 9)
     assert np.array_equal(np.asarray(a), [[9, -1, -1], [5, 6, 7], [-1, -1, -1]])
     assert a.shape() == (3, 3) and a[1][2] == 7
+
+
+def test_cc_alt_variant_is_rejected_like_it_fails_in_the_reference():
+    """CCStencilKsiFaces divides by KSI.n_PQ (0 for axis-aligned stencils): NaN in the reference
+    itself ("Currently Inoperable").  We refuse it instead of producing NaN."""
+    case = golden.Case("cc_ldc_upwind")
+    m = fb.Mesher()
+    m.import_meshpy(case.raw())
+    m.calc_mesh_properties()
+    with pytest.raises(ValueError, match="cc_alt_upwind"):
+        m.to_env(fb.D2Q9(0.8, 0.1), flux_method="cc_alt_upwind")
+    with pytest.raises(ValueError, match="Unsupported flux method"):
+        m.to_env(fb.D2Q9(0.8, 0.1), flux_method="weno")
+    cells, faces, nodes = case.containers()
+    faces.npq = np.zeros_like(faces.n)
+    with pytest.raises(ValueError, match="CCStencilKsiFaces"):
+        fb.Environment(cells, faces, nodes)._describe()
