@@ -39,6 +39,7 @@ nodes = mesher.set_rho_node(nodes, marker=2, rho=rho)
 
 env = Environment(cells, faces, nodes)                         # notebook c16
 env.init()
+env.build()                                                    # engine creation (context, upload) outside the timing
 t0 = time.time()
 chunk = 1000
 for i in range(args.steps // chunk):                           # notebook c17: for i in tqdm(range(100000)): env = env.step()

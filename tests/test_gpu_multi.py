@@ -150,7 +150,7 @@ def test_native_nccl_general_partition_equals_single_handle():
     single.close()
 
 
-def _native_worker(rank, world, port, q):
+def _native_worker(rank, world, port, q, native=True):
     import os, sys
     import numpy as np
     import torch
@@ -158,15 +158,18 @@ def _native_worker(rank, world, port, q):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("gloo", rank=rank, world_size=world)       # plumbing only; data path = engine NCCL
+    # native: torch.distributed is plumbing only (gloo), the data path is the engine's own NCCL
+    # communicator; otherwise the halo buffers travel through torch.distributed P2P (NCCL backend)
+    dist.init_process_group("gloo" if native else "cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     try:
         import fvdbm_jax_b200 as fb
         from fvdbm_jax_b200.distributed import DistributedEnvironment, strip_local_mesh
         dyn = fb.D2Q9(0.8, 0.1)
         nx, nyr = 40, 24
         local, fpc = strip_local_mesh(nx, nyr, rank, world, dyn, "lax_wendroff")
-        denv = DistributedEnvironment(local, dyn, "lax_wendroff", np.float32, rank, 2 * nx * nyr * world, fpc, native=True)
+        denv = DistributedEnvironment(local, dyn, "lax_wendroff", np.float32, rank, 2 * nx * nyr * world, fpc, native=native)
         denv.step(20)
+        denv.sync()
         pdf = np.array(denv.env.cells.pdf[:local.n_owned])
         q.put((rank, local.cell_gid[:local.n_owned].copy(), pdf))
         denv.close()
@@ -176,8 +179,10 @@ def _native_worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(600)
-def test_native_nccl_exchange_equals_single_handle():
-    """Real multi-GPU path (engine-owned NCCL communicator, one process per GPU) == one handle."""
+@pytest.mark.parametrize("native", [True, False])
+def test_native_nccl_exchange_equals_single_handle(native):
+    """Real multi-GPU path (engine-owned NCCL communicator, or torch.distributed P2P driven from
+    Python; one process per GPU) == one handle."""
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -193,7 +198,8 @@ def test_native_nccl_exchange_equals_single_handle():
     q = ctx.Queue()
     import os
     port = 29700 + os.getpid() % 1000
-    procs = [ctx.Process(target=_native_worker, args=(r, world, port, q)) for r in range(world)]
+    port += 0 if native else 17
+    procs = [ctx.Process(target=_native_worker, args=(r, world, port, q, native)) for r in range(world)]
     for p in procs:
         p.start()
     got = np.zeros_like(ref)

@@ -38,7 +38,11 @@ def main():
         cfgs = [dict(variant=1), dict(variant=2, tile=256, stages=3), dict(variant=2, tile=256, stages=3, reverse=1)]
     for reorder in args.reorders.split(","):
         t0 = time.time()
-        env = fb.Environment(cells, faces, nodes, dtype=real, reorder=reorder)
+        if reorder == "random":       # worst case: what an arbitrarily numbered unstructured mesh looks like
+            reorder_arg = np.random.default_rng(0).permutation(n).astype(np.int32)
+        else:
+            reorder_arg = reorder
+        env = fb.Environment(cells, faces, nodes, dtype=real, reorder=reorder_arg)
         env.init(); env.build()
         t_build = time.time() - t0
         for cfg in (cfgs if reorder == "hilbert" else cfgs[:1] + [c for c in cfgs if c.get("variant") == 2 and c.get("tile") == 256 and c.get("stages") == 3][:2]):
