@@ -28,7 +28,7 @@ VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA = 0, 1, 2
 
 EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_error", "fvdbm_step",
            "fvdbm_step_timed", "fvdbm_sync", "fvdbm_get", "fvdbm_set", "fvdbm_set_params",
-           "fvdbm_set_option", "fvdbm_info", "fvdbm_halo_set_lists", "fvdbm_halo_pack",
+           "fvdbm_set_option", "fvdbm_info", "fvdbm_check_finite", "fvdbm_halo_set_lists", "fvdbm_halo_pack",
            "fvdbm_halo_unpack", "fvdbm_step_phase", "fvdbm_stream", "fvdbm_comm_unique_id", "fvdbm_comm_init",
            "fvdbm_halo_set_peers", "fvdbm_plan_create",
            "fvdbm_plan_destroy", "fvdbm_plan_array", "fvdbm_plan_scalar")
@@ -80,6 +80,8 @@ def load():
     lib.fvdbm_set_params.argtypes = [H, C.c_double, C.c_double]
     lib.fvdbm_set_option.argtypes = [H, C.c_int, C.c_int64]
     lib.fvdbm_info.argtypes = [H, C.c_int, C.POINTER(C.c_int64)]
+    lib.fvdbm_check_finite.argtypes = [H, C.POINTER(C.c_int64)]
+    lib.fvdbm_check_finite.restype = C.c_int
     lib.fvdbm_halo_set_lists.argtypes = [H, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
     lib.fvdbm_halo_pack.argtypes = [H, C.c_void_p]
     lib.fvdbm_halo_unpack.argtypes = [H, C.c_void_p]

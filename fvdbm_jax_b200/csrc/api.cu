@@ -72,6 +72,7 @@ struct Engine {
     virtual int set_params(double tau, double dt) = 0;
     virtual int set_option(int opt, int64_t v) = 0;
     virtual int info(int key, int64_t* v) const = 0;
+    virtual int check_finite(int64_t* bad) = 0;
     virtual int halo_set_lists(const int32_t* s, int64_t ns, const int32_t* r, int64_t nr) = 0;
     virtual int halo_pack(void* buf) = 0;
     virtual int halo_unpack(const void* buf) = 0;
@@ -144,6 +145,7 @@ struct EngineT final : Engine {
     DevBuf<real> s_rho, s_ux, s_uy, s_feq, s_flux;     // staged dynamics (lazy)
     DevBuf<real> scratch;                              // export/import staging
     DevBuf<int32_t> halo_send, halo_recv;
+    DevBuf<unsigned long long> counter;
     // native exchange (optional)
     ncclComm_t comm = nullptr;
     std::vector<int> send_peers, recv_peers;
@@ -652,6 +654,21 @@ struct EngineT final : Engine {
         }
     }
 
+    int check_finite(int64_t* bad) override {
+        CU_TRY(cudaSetDevice(device));
+        if (!bad) { err = "null argument"; return FVDBM_ERR_ARG; }
+        if (!counter.p) CU_TRY(counter.alloc(1));
+        CU_TRY(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), stream));
+        k_count_nonfinite<real, Q><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(pdf[cur].p, ipos.p, plan.Npad, plan.No, counter.p);
+        ++launches;
+        CU_TRY(cudaGetLastError());
+        unsigned long long host = 0;
+        CU_TRY(cudaMemcpyAsync(&host, counter.p, sizeof(host), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        *bad = (int64_t)host;
+        return FVDBM_OK;
+    }
+
     int set_params(double tau, double dt) override {
         if (!(tau > 0)) { err = "tau must be positive"; return FVDBM_ERR_ARG; }
         P.inv_tau = (real)(1.0 / tau);
@@ -826,6 +843,7 @@ int fvdbm_set(fvdbm_handle* h, int field, const void* src, size_t bytes) { retur
 int fvdbm_set_params(fvdbm_handle* h, double tau, double dt) { return h ? h->e->set_params(tau, dt) : FVDBM_ERR_ARG; }
 int fvdbm_set_option(fvdbm_handle* h, int opt, int64_t v) { return h ? h->e->set_option(opt, v) : FVDBM_ERR_ARG; }
 int fvdbm_info(const fvdbm_handle* h, int key, int64_t* v) { return h ? h->e->info(key, v) : FVDBM_ERR_ARG; }
+int fvdbm_check_finite(fvdbm_handle* h, int64_t* bad) { return h ? h->e->check_finite(bad) : FVDBM_ERR_ARG; }
 int fvdbm_halo_set_lists(fvdbm_handle* h, const int32_t* s, int64_t ns, const int32_t* r, int64_t nr) {
     return h ? h->e->halo_set_lists(s, ns, r, nr) : FVDBM_ERR_ARG;
 }

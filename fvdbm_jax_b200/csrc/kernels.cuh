@@ -467,6 +467,24 @@ __global__ void k_export_moments(const Params<real> P, const real* __restrict__ 
     }
 }
 
+// failure detection: count owned cells with a non-finite population (one atomic per warp)
+template <typename real, int Q>
+__global__ void k_count_nonfinite(const real* __restrict__ pdf, const int32_t* __restrict__ ipos, int64_t Npad, int64_t No,
+                                  unsigned long long* __restrict__ count) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (c < Npad) {
+        const int32_t o = ipos[c];
+        if (o >= 0 && o < No) {
+            const real* p = pdf + pdf_index<Q>(c);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) bad |= !isfinite(p[q * kTW]);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
 // halo exchange helpers: list[i] = position ; buf layout [count][Q]
 template <typename real, int Q>
 __global__ void k_pack(const real* __restrict__ pdf, const int32_t* __restrict__ list, int64_t n, real* __restrict__ buf) {

@@ -242,6 +242,14 @@ class Environment:
         _lib.check(self._lib.fvdbm_set_params(self._handle, float(tau), float(delta_t)), self._handle)
         return self
 
+    def count_nonfinite(self) -> int:
+        """Number of cells whose populations hold a NaN/Inf (the reference has no such check: a
+        diverged run is only visible in the plots)."""
+        self.build()
+        v = C.c_int64()
+        _lib.check(self._lib.fvdbm_check_finite(self._handle, C.byref(v)), self._handle)
+        return int(v.value)
+
     def info(self, key: int) -> int:
         self.build()
         v = C.c_int64()

@@ -151,6 +151,9 @@ int  fvdbm_set(fvdbm_handle* h, int field, const void* src, size_t bytes);
 int  fvdbm_set_params(fvdbm_handle* h, double tau, double delta_t);
 int  fvdbm_set_option(fvdbm_handle* h, int option, int64_t value);
 int  fvdbm_info(const fvdbm_handle* h, int key, int64_t* value);
+/* failure detection (the reference only shows blow-ups in plots): number of owned cells whose current
+   populations contain a NaN / Inf; one small reduction kernel, blocks until the count is known */
+int  fvdbm_check_finite(fvdbm_handle* h, int64_t* nonfinite_cells);
 
 /* ---- multi-GPU halo plumbing (one handle per rank; cells [N_owned,N) are halo copies) -------
  * Send lists are given in the caller's ORIGINAL local numbering; the library translates.

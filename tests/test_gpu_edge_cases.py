@@ -129,3 +129,16 @@ def test_upwind_axis_aligned_faces_where_ksi_dot_n_is_zero():
     env.init()
     compare(env.step(10), o, 1e-11)
     env.close()
+
+
+def test_divergence_is_detected():
+    """tau < 0.5 is unstable: the run blows up and count_nonfinite() reports it."""
+    case = golden.Case("ldc_tri_lw")
+    env = fb.Environment(*case.containers(), dtype=np.float32)
+    env.init()
+    assert env.step(5).count_nonfinite() == 0
+    env.set_params(0.05, 1.0)
+    env = env.step(400)
+    bad = env.count_nonfinite()
+    assert bad > 0 and bad == int(np.count_nonzero(~np.isfinite(env.cells.pdf).all(axis=1)))
+    env.close()
