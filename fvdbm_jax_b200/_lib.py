@@ -233,5 +233,5 @@ class HostPlan:
             pass
 
 
-_PLAN_I32 = {"pos", "ipos", "ccode", "cface", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
+_PLAN_I32 = {"pos", "ipos", "ccode", "cface", "bt_off", "bt_nodes", "bf_la", "bf_lb", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
              "ring_cell", "s_cface", "s_csign", "s_fcell", "s_fnode"}

@@ -124,6 +124,11 @@ struct GhostTables {
     const real* bf_ratio;
     const real* npdf;      // SoA [Q][NTpad]
     int64_t NTpad;
+    // border kernel only: node values staged per tile in shared memory, [slot][Q]; bf_la/bf_lb give
+    // the slots of a boundary side's two nodes (null/unused elsewhere)
+    const real* snode = nullptr;
+    const int32_t* bf_la = nullptr;
+    const int32_t* bf_lb = nullptr;
 };
 
 // One cell of the fused step: K sides (neighbour populations through `load_nbr(pos, fn)`, ghosts
@@ -150,12 +155,22 @@ FVDBM_HD void advance_cell(const Params<real>& P, const GhostTables<real>& G, co
         } else {
             v = -(cd + 1);
             const int32_t b = v >> 2;
-            const int32_t na = FVDBM_LDG(G.bf_na + b), nb = FVDBM_LDG(G.bf_nb + b);
             const real ratio = FVDBM_LDG(G.bf_ratio + b);
+            if (G.snode) {                      // node values staged by this tile (k_border)
+                const real* ga = G.snode + (size_t)FVDBM_LDG(G.bf_la + b) * Q;
+                const real* gb = G.snode + (size_t)FVDBM_LDG(G.bf_lb + b) * Q;
 #pragma unroll
-            for (int q = 1; q < Q; ++q) {       // containers.py:285-287: mean of the two node PDFs, extrapolated
-                const real g = (FVDBM_LDG(G.npdf + q * G.NTpad + na) + FVDBM_LDG(G.npdf + q * G.NTpad + nb)) / real(2);
-                fn[q] = g + (g - f[q]) * ratio;
+                for (int q = 1; q < Q; ++q) {
+                    const real g = (ga[q] + gb[q]) / real(2);
+                    fn[q] = g + (g - f[q]) * ratio;
+                }
+            } else {
+                const int32_t na = FVDBM_LDG(G.bf_na + b), nb = FVDBM_LDG(G.bf_nb + b);
+#pragma unroll
+                for (int q = 1; q < Q; ++q) {   // containers.py:285-287: mean of the two node PDFs, extrapolated
+                    const real g = (FVDBM_LDG(G.npdf + q * G.NTpad + na) + FVDBM_LDG(G.npdf + q * G.NTpad + nb)) / real(2);
+                    fn[q] = g + (g - f[q]) * ratio;
+                }
             }
         }
         fn[0] = real(0);

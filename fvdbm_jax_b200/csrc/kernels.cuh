@@ -281,11 +281,11 @@ __device__ __forceinline__ real warp_sum(real v) {
     return v;
 }
 
+// One active node evaluated by one warp: lanes walk the ring, shfl_xor tree reduction (every lane ends
+// with the same sums), then rho / vel / populations of the node (identical on all lanes).
 template <typename real, int Q>
-__global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
-    const int node = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (node >= a.NA) return;
+__device__ __forceinline__ void warp_eval_node(const NodeArgs<real>& a, int node, int lane, real& rho_n, real& ux_n, real& uy_n,
+                                               real* pdf_n) {
     const int beg = a.ring_off[node], end = a.ring_off[node + 1];
     real sw = real(0), srho = real(0), sux = real(0), suy = real(0);
     real sneq[Q];
@@ -303,17 +303,107 @@ __global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
     sw = warp_sum(sw); srho = warp_sum(srho); sux = warp_sum(sux); suy = warp_sum(suy);
 #pragma unroll
     for (int q = 0; q < Q; ++q) sneq[q] = warp_sum(sneq[q]);
+    rho_n = a.nrho[node]; ux_n = a.nvel[node]; uy_n = a.nvel[a.NTpad + node];
+    node_finish<real, Q>(a.P, a.tn_type[node], sw, srho, sux, suy, sneq, rho_n, ux_n, uy_n, pdf_n);
+}
+
+template <typename real, int Q>
+__device__ __forceinline__ void store_node(const NodeArgs<real>& a, int node, real rho_n, real ux_n, real uy_n, const real* pdf_n) {
     const int type = a.tn_type[node];
-    real rho_n = a.nrho[node], ux_n = a.nvel[node], uy_n = a.nvel[a.NTpad + node];
-    real pdf_n[Q];
-    node_finish<real, Q>(a.P, type, sw, srho, sux, suy, sneq, rho_n, ux_n, uy_n, pdf_n);
-    __syncwarp();
-    if (lane == 0) {
-        if (type == 1) a.nrho[node] = rho_n;
-        if (type == 2) { a.nvel[node] = ux_n; a.nvel[a.NTpad + node] = uy_n; }
+    if (type == 1) a.nrho[node] = rho_n;
+    if (type == 2) { a.nvel[node] = ux_n; a.nvel[a.NTpad + node] = uy_n; }
 #pragma unroll
-        for (int q = 0; q < Q; ++q) a.npdf[q * a.NTpad + node] = pdf_n[q];
+    for (int q = 0; q < Q; ++q) a.npdf[q * a.NTpad + node] = pdf_n[q];
+}
+
+template <typename real, int Q>
+__global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
+    const int node = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (node >= a.NA) return;
+    real rho_n, ux_n, uy_n, pdf_n[Q];
+    warp_eval_node<real, Q>(a, node, lane, rho_n, ux_n, uy_n, pdf_n);
+    __syncwarp();
+    if (lane == 0) store_node<real, Q>(a, node, rho_n, ux_n, uy_n, pdf_n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Border kernel: one CTA per tile of BORDER_TILE (=256) border cells.  Phase A: the tile's warps
+// evaluate the boundary nodes its ghost sides reference (S3) into shared memory -- a node shared by
+// two tiles is evaluated by both, identically -- and publish them for observation; phase B: the
+// tile's cells run the ordinary fused update taking ghost populations from shared memory.  This
+// keeps ONE kernel on the per-step critical path [nodes -> border cells] while the interior cells
+// run on the side stream.
+// ------------------------------------------------------------------------------------------------
+template <typename real>
+struct BorderArgs {
+    FusedArgs<real> F;
+    NodeArgs<real> N;
+    const int32_t* __restrict__ bt_off;
+    const int32_t* __restrict__ bt_nodes;
+    const int32_t* __restrict__ bf_la;
+    const int32_t* __restrict__ bf_lb;
+};
+
+template <typename real, int Q, int K, int SCHEME>
+__global__ void __launch_bounds__(256) k_border(const BorderArgs<real> b) {
+    constexpr int NC = SCHEME == 0 ? 2 : 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* s_node = reinterpret_cast<real*>(smem_raw);
+    const FusedArgs<real>& a = b.F;
+    const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = b.bt_off[tile], nn = b.bt_off[tile + 1] - n0;
+    for (int i = warp; i < nn; i += 8) {
+        const int t = b.bt_nodes[n0 + i];
+        if (t < b.N.NA) {                                   // active: evaluate from its ring
+            real rho_n, ux_n, uy_n, pdf_n[Q];
+            warp_eval_node<real, Q>(b.N, t, lane, rho_n, ux_n, uy_n, pdf_n);
+            if (lane == 0) {
+                store_node<real, Q>(b.N, t, rho_n, ux_n, uy_n, pdf_n);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) s_node[i * Q + q] = pdf_n[q];
+            }
+        } else if (lane < Q) {                              // type-0 boundary node: keeps its stored PDFs
+            s_node[i * Q + lane] = b.N.npdf[lane * b.N.NTpad + t];
+        }
     }
+    __syncthreads();
+    const int64_t c = a.cell_begin + (int64_t)tile * blockDim.x + threadIdx.x;
+    if (c >= a.cell_end) return;
+    const size_t mt = (size_t)(c >> 5);
+    const int32_t* gc = a.ccode + mt * (K * kTW) + lane;
+    int32_t code[K];
+    code[0] = gc[0];
+    if (code[0] == kHole) return;
+#pragma unroll
+    for (int k = 1; k < K; ++k) code[k] = gc[k * kTW];
+    real coef[K * NC];
+    if (a.cface == nullptr) {
+        const real* gco = a.ccoef + mt * (K * NC * kTW) + lane;
+#pragma unroll
+        for (int i = 0; i < K * NC; ++i) coef[i] = gco[i * kTW];
+    } else {
+        const int32_t* gf = a.cface + mt * (K * kTW) + lane;
+#pragma unroll
+        for (int k = 0; k < K; ++k) load_face_record<real, NC>(a.fcoef, gf[k * kTW], coef + k * NC);
+    }
+    const real* pin = a.pdf_in;
+    const real* gp = pin + mt * (Q * kTW) + lane;
+    real f[Q], out[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) f[q] = gp[q * kTW];
+    auto load_nbr = [pin](int64_t nb, real* fn) {
+        const real* pn = pin + pdf_index<Q>(nb);
+#pragma unroll
+        for (int q = 1; q < Q; ++q) fn[q] = __ldg(pn + q * kTW);
+    };
+    GhostTables<real> G = a.G;
+    G.snode = s_node; G.bf_la = b.bf_la; G.bf_lb = b.bf_lb;
+    advance_cell<real, Q, K, SCHEME>(a.P, G, f, code, coef, load_nbr, out);
+    real* go = a.pdf_out + mt * (Q * kTW) + lane;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) go[q * kTW] = out[q];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -32,6 +32,7 @@ namespace fvdbm {
 constexpr int TW = 32;            // lanes of one AoSoA mini-tile
 constexpr int PAD_TO = 512;       // group alignment = largest CTA tile
 constexpr int32_t HOLE = INT32_MIN;
+constexpr int BORDER_TILE = 256;  // cells per CTA of the border kernel
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -49,7 +50,11 @@ struct Plan {
     int64_t NB = 0;
     std::vector<int32_t> bf_na, bf_nb;
     std::vector<real> bf_ratio;
-    int64_t NT = 0, NTpad = 0, NA = 0;          // tracked nodes, active (type != 0) tracked nodes
+    int64_t NT = 0, NTpad = 0, NA = 0, NO = 0;  // tracked nodes; [0,NA) active (type != 0); [0,NO) active "orphans"
+                                                // not on any owned boundary side (only those need k_nodes when fused)
+    // border tiles (BORDER_TILE cells each, from Bstart): the tracked nodes each tile's boundary sides use
+    std::vector<int32_t> bt_off, bt_nodes, bf_la, bf_lb;
+    int64_t max_tile_nodes = 0;
     std::vector<int32_t> tn_orig, tn_type, node_track, tn_active, ring_off, ring_cell;
     std::vector<real> ring_w, tn_pdf, tn_rho, tn_vel;
     std::vector<int32_t> s_cface, s_csign, s_fcell, s_fnode;
@@ -153,16 +158,29 @@ struct Plan {
                     int32_t n = d.face_node_idx[2 * j + e];
                     if (n >= 0 && n < P) want[n] = 1;
                 }
-        // active nodes first so the node kernel covers a dense prefix
-        tn_orig.clear(); tn_type.clear();
-        for (int pass = 0; pass < 2; ++pass)
-            for (int64_t n = 0; n < P; ++n)
-                if (want[n] && ((d.node_type[n] != 0) == (pass == 0))) {
-                    node_track[n] = (int32_t)tn_orig.size();
-                    tn_orig.push_back((int32_t)n);
-                    tn_type.push_back(d.node_type[n]);
-                    if (pass == 0) ++NA;
-                }
+        // order: active orphans | active nodes on an owned boundary side (evaluated by the border kernel,
+        // tile by tile) | inactive tracked nodes (keep their stored PDFs)
+        std::vector<uint8_t> on_side(P, 0);
+        if (fused_ok)
+            for (int64_t c = 0; c < No; ++c)
+                for (int k = 0; k < K; ++k)
+                    if (other[c * K + k] == -1) {
+                        const int64_t j = d.cell_face_idx[c * K + k];
+                        on_side[d.face_node_idx[2 * j]] = 1; on_side[d.face_node_idx[2 * j + 1]] = 1;
+                    }
+        tn_orig.clear(); tn_type.clear(); NA = 0; NO = 0;
+        for (int pass = 0; pass < 3; ++pass)
+            for (int64_t n = 0; n < P; ++n) {
+                if (!want[n]) continue;
+                const bool active = d.node_type[n] != 0;
+                const int cls = !active ? 2 : (on_side[n] ? 1 : 0);
+                if (cls != pass) continue;
+                node_track[n] = (int32_t)tn_orig.size();
+                tn_orig.push_back((int32_t)n);
+                tn_type.push_back(d.node_type[n]);
+                if (active) ++NA;
+                if (cls == 0) ++NO;
+            }
         NT = (int64_t)tn_orig.size();
         NTpad = round_up(std::max<int64_t>(NT, 1), TW);
         const real* npdf = static_cast<const real*>(d.node_pdf);
@@ -227,6 +245,15 @@ struct Plan {
             //   face layout: fcoef[rec][NC] + cface[tile][k][lane] -> rec (one 16 B record per face, shared by
             //                both cells; records numbered by first touch in position order for locality)
             cface.assign((size_t)ntile * K * TW, 0);
+            const int64_t nbt = (round_up(Oend, PAD_TO) - Bstart) / BORDER_TILE;
+            bt_off.assign(nbt + 1, 0); bt_nodes.clear(); bf_la.clear(); bf_lb.clear(); max_tile_nodes = 0;
+            std::vector<int32_t> slot_of(std::max<int64_t>(NT, 1), -1), stamp(std::max<int64_t>(NT, 1), -1);
+            int64_t cur_bt = -1;
+            auto tile_slot = [&](int64_t bt, int32_t t) -> int32_t {   // slot of tracked node t in border tile bt
+                while (cur_bt < bt) { ++cur_bt; bt_off[cur_bt] = (int32_t)bt_nodes.size(); }
+                if (stamp[t] != (int32_t)bt) { stamp[t] = (int32_t)bt; slot_of[t] = (int32_t)(bt_nodes.size() - bt_off[bt]); bt_nodes.push_back(t); }
+                return slot_of[t];
+            };
             std::vector<int32_t> rec_of(F, -1);
             fcoef.clear();
             NF = 0;
@@ -243,9 +270,13 @@ struct Plan {
                     if (o >= 0) code = (pos[o] << 2) | (neg << 1) | sl;
                     else {
                         const real dg = fdist[2 * j + (1 - sl)], dk = fdist[2 * j + sl];
-                        bf_na.push_back(node_track[d.face_node_idx[2 * j]]);
-                        bf_nb.push_back(node_track[d.face_node_idx[2 * j + 1]]);
+                        const int32_t ta = node_track[d.face_node_idx[2 * j]], tb = node_track[d.face_node_idx[2 * j + 1]];
+                        bf_na.push_back(ta);
+                        bf_nb.push_back(tb);
                         bf_ratio.push_back(dg / dk);
+                        const int64_t bt = (pc - Bstart) / BORDER_TILE;       // boundary cells live in the border group
+                        bf_la.push_back(tile_slot(bt, ta));
+                        bf_lb.push_back(tile_slot(bt, tb));
                         code = -(int32_t)(((NB << 2) | (neg << 1) | sl) + 1);
                         ++NB;
                     }
@@ -267,6 +298,8 @@ struct Plan {
                     cface[(size_t)(tile * K + k) * TW + lane] = rec_of[j];
                 }
             }
+            while (cur_bt < nbt) { ++cur_bt; bt_off[cur_bt] = (int32_t)bt_nodes.size(); }
+            for (int64_t t = 0; t < nbt; ++t) max_tile_nodes = std::max<int64_t>(max_tile_nodes, bt_off[t + 1] - bt_off[t]);
             if (NB >= (int64_t(1) << 28)) return fail("too many boundary sides");
         }
         return true;

@@ -78,8 +78,27 @@ def test_host_plan_layout(name):
     want = set(np.nonzero(typ != 0)[0].tolist()) | set(case.static["faces.nodes_index"][ghost_faces].reshape(-1).tolist())
     tn = hp.array("tn_orig")
     assert set(tn.tolist()) == want and hp.scalar("NT") == len(want)
-    na = hp.scalar("NA")
+    na, no = hp.scalar("NA"), hp.scalar("NO")
     assert np.all(typ[tn[:na]] != 0) and np.all(typ[tn[na:]] == 0)
+    # border tiles: every boundary side finds its two nodes in its tile's node list; orphans (active
+    # nodes no owned boundary side references) come first and are in no tile list
+    bt_off, bt_nodes = hp.array("bt_off"), hp.array("bt_nodes")
+    bf_na, bf_nb, bf_la, bf_lb = (hp.array(k) for k in ("bf_na", "bf_nb", "bf_la", "bf_lb"))
+    b = 0
+    for p in range(Bstart, Npad):                       # boundary sides are numbered in position order
+        if ipos[p] < 0:
+            continue
+        tile = (p - Bstart) // 256
+        for k in range(K):
+            cd = int(code[p >> 5, k, p & 31])
+            if cd < 0 and cd != np.iinfo(np.int32).min:
+                assert (-(cd + 1)) >> 2 == b
+                lst = bt_nodes[bt_off[tile]:bt_off[tile + 1]]
+                assert lst[bf_la[b]] == bf_na[b] and lst[bf_lb[b]] == bf_nb[b]
+                b += 1
+    assert b == hp.scalar("NB")
+    assert hp.scalar("max_tile_nodes") == int(np.max(np.diff(bt_off))) if bt_off.size > 1 else True
+    assert not (set(range(no)) & set(bt_nodes.tolist()))
     hp.close()
 
 
