@@ -146,7 +146,9 @@ struct EngineT final : Engine {
     DevBuf<real> scratch;                              // export/import staging
     DevBuf<int32_t> halo_send, halo_recv, bt_off, bt_nodes, bf_la, bf_lb;
     DevBuf<unsigned long long> counter;
-    int border_fused = 1;                // 1: k_border (nodes + border cells in one kernel); 0: k_nodes then the cell kernel
+    int border_fused = 0;                // 0 (default): k_nodes, then the cell kernel over the border tiles;
+                                         // 1: k_border, both in one launch -- measured 9x SLOWER on small meshes
+                                         // (per-tile node evaluation serialises the latency chains)
     // native exchange (optional)
     ncclComm_t comm = nullptr;
     std::vector<int> send_peers, recv_peers;
