@@ -112,7 +112,9 @@ def test_fused_variants_bitwise_identical():
                dict(variant=_lib.VARIANT_TMA, tile=256, stages=4, reverse=1, graph=4),
                dict(variant=_lib.VARIANT_DIRECT, reverse=1, graph=2, reorder="hilbert"),
                dict(variant=_lib.VARIANT_TMA, tile=128, stages=4, reorder="rcm", ctas=1)]
+    configs.append(dict(variant=_lib.VARIANT_DIRECT, border_fused=1))      # k_border experiment path stays correct
     for cfg in configs:
+        os.environ["FVDBM_BORDER_FUSED"] = str(cfg.get("border_fused", 0))
         env = fb.Environment(cells, faces, nodes, dtype=np.float32, reorder=cfg.get("reorder", "none"))
         env.init()
         env.set_option(_lib.OPT_VARIANT, cfg["variant"])
@@ -128,6 +130,7 @@ def test_fused_variants_bitwise_identical():
             for a, b in zip(ref, got):
                 np.testing.assert_array_equal(a, b, err_msg=str(cfg))
         env.close()
+    os.environ.pop("FVDBM_BORDER_FUSED", None)
 
 
 def test_rest_state_fixed_point_and_exact_conservation():
