@@ -161,7 +161,7 @@ def workload_config(args, nx, cells, inner):
     return {"workload": f"synthetic triangulated square, {shape}, x-periodic + y walls (lid 0.1), D2Q9 tau=0.8 dt=0.1, {args.scheme}",
             "inner_iterations_per_step": inner, "scheme": args.scheme, "l2": "inputs exceed L2 (no flush needed)",
             "reorder": args.reorder, "variant": args.variant, "tile_cells": args.tile, "stages": args.stages,
-            "reverse_sweep": args.reverse, "graph_steps": args.graph}
+            "reverse_sweep": args.reverse, "graph_steps": args.graph, "temporal": getattr(args, "temporal", -1)}
 
 
 def main():
@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--reverse", type=int, default=-1)
     ap.add_argument("--graph", type=int, default=-1)
     ap.add_argument("--ctas", type=int, default=-1)
+    ap.add_argument("--temporal", type=int, default=-1, help="1: temporal blocking (two iterations per pass), single GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-nx", type=int, default=1000)
@@ -240,7 +241,8 @@ def main():
     for opt, val in ((_lib.OPT_VARIANT, args.variant), (_lib.OPT_TILE_CELLS, args.tile), (_lib.OPT_STAGES, args.stages)):
         if val > 0:
             stepper.set_option(opt, val)
-    for opt, val in ((_lib.OPT_REVERSE_SWEEP, args.reverse), (_lib.OPT_GRAPH_STEPS, args.graph), (_lib.OPT_CTAS_PER_SM, args.ctas)):
+    for opt, val in ((_lib.OPT_REVERSE_SWEEP, args.reverse), (_lib.OPT_GRAPH_STEPS, args.graph), (_lib.OPT_CTAS_PER_SM, args.ctas),
+                     (_lib.OPT_TEMPORAL, args.temporal if world == 1 else -1)):
         if val >= 0:
             stepper.set_option(opt, val)
 

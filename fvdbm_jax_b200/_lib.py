@@ -24,7 +24,8 @@ VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA = 0, 1, 2
  CELL_PDF_PREV) = range(9)
 (INFO_MODE, INFO_STEPS, INFO_LAUNCHES, INFO_TRACKED_NODES, INFO_BOUNDARY_SIDES, INFO_DEVICE_BYTES,
  INFO_VARIANT, INFO_NPAD, INFO_FUSED_OK, INFO_HALO_CELLS, INFO_OWNED_CELLS) = range(11)
-(OPT_VARIANT, OPT_TILE_CELLS, OPT_STAGES, OPT_GRAPH_STEPS, OPT_CTAS_PER_SM, OPT_REVERSE_SWEEP) = range(6)
+(OPT_VARIANT, OPT_TILE_CELLS, OPT_STAGES, OPT_GRAPH_STEPS, OPT_CTAS_PER_SM, OPT_REVERSE_SWEEP,
+ OPT_TEMPORAL) = range(7)
 
 EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_error", "fvdbm_step",
            "fvdbm_step_timed", "fvdbm_sync", "fvdbm_get", "fvdbm_set", "fvdbm_set_params",
@@ -233,5 +234,5 @@ class HostPlan:
             pass
 
 
-_PLAN_I32 = {"pos", "ipos", "ccode", "cface", "bt_off", "bt_nodes", "bf_la", "bf_lb", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
+_PLAN_I32 = {"t2_off", "t2_n1", "t2_pos", "l2_list", "pos", "ipos", "ccode", "cface", "bt_off", "bt_nodes", "bf_la", "bf_lb", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
              "ring_cell", "s_cface", "s_csign", "s_fcell", "s_fnode"}

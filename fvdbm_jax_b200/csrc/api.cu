@@ -134,7 +134,14 @@ struct EngineT final : Engine {
     int64_t steps = 0, launches = 0;
     bool phase0_done = false;
 
-    DevBuf<real> pdf[2];
+    DevBuf<real> pdf[3];                 // ping-pong (2) or, with temporal blocking, a 3-buffer rotation
+    int nbuf = 2, prev = 1;              // prev = buffer holding the populations before the last iteration
+    int temporal = 0;                    // 1: two iterations per pass over overlapped tiles (k_fused2)
+    DevBuf<int32_t> t2_off, t2_n1, t2_pos, l2_list;
+    DevBuf<int64_t> t2_loff;
+    DevBuf<uint16_t> t2_lnbr;
+    size_t t2_smem = 0;
+    int nxt() const { return (cur + 1) % nbuf; }
     DevBuf<int32_t> ccode, bf_na, bf_nb, pos, ipos, ring_off, ring_cell, tn_type;
     DevBuf<real> ccoef, fcoef, bf_ratio, ring_w, npdf, nrho, nvel;
     DevBuf<int32_t> cface;
@@ -221,6 +228,15 @@ struct EngineT final : Engine {
             CU_TRY(bf_na.upload(plan.bf_na, stream));
             CU_TRY(bf_nb.upload(plan.bf_nb, stream));
             CU_TRY(bf_ratio.upload(plan.bf_ratio, stream));
+            if (plan.t2_ok) {
+                CU_TRY(t2_off.upload(plan.t2_off, stream)); CU_TRY(t2_n1.upload(plan.t2_n1, stream));
+                CU_TRY(t2_pos.upload(plan.t2_pos, stream)); CU_TRY(t2_loff.upload(plan.t2_loff, stream));
+                CU_TRY(t2_lnbr.upload(plan.t2_lnbr, stream)); CU_TRY(l2_list.upload(plan.l2_list, stream));
+                s0_stride = (int)round_up(plan.t2_max_entries, 32); s1_stride = (int)round_up(plan.t2_max_n01, 32);
+                t2_smem = (size_t)Q * (s0_stride + s1_stride) * sizeof(real);
+                CU_TRY(cudaFuncSetAttribute(k_fused2<real, Q, K, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)prop.sharedMemPerBlockOptin));
+            }
             CU_TRY(bt_off.upload(plan.bt_off, stream));
             CU_TRY(bt_nodes.upload(plan.bt_nodes, stream));
             CU_TRY(bf_la.upload(plan.bf_la, stream));
@@ -248,7 +264,7 @@ struct EngineT final : Engine {
         CU_TRY(cudaStreamSynchronize(stream));
         // host staging vectors are no longer needed
         plan.ccode = {}; plan.ccoef = {}; plan.cface = {}; plan.fcoef = {}; plan.s_cface = {}; plan.s_csign = {}; plan.s_fcell = {}; plan.s_fnode = {};
-        plan.ring_cell = {}; plan.ring_w = {}; plan.tn_pdf = {}; plan.bt_nodes = {}; plan.bf_la = {}; plan.bf_lb = {};
+        plan.ring_cell = {}; plan.ring_w = {}; plan.tn_pdf = {}; plan.t2_pos = {}; plan.t2_lnbr = {}; plan.bt_nodes = {}; plan.bf_la = {}; plan.bf_lb = {};
         int rc = set(FVDBM_CELL_PDF, d.cell_pdf, (size_t)plan.N * Q * sizeof(real));
         if (rc) return rc;
         // opt-in shared memory for the TMA kernel
@@ -265,10 +281,12 @@ struct EngineT final : Engine {
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
+        if (const char* e = getenv("FVDBM_TEMPORAL")) { int rc2 = set_temporal(atoi(e)); if (rc2) return rc2; }
         if (variant == FVDBM_VARIANT_AUTO) variant = FVDBM_VARIANT_DIRECT;
         return sanitize_options();
     }
     size_t max_smem = 0, border_smem = 0;
+    int s0_stride = 0, s1_stride = 0;
     int occ_cache = 0;
 
     size_t stage_bytes(int tc) const {
@@ -290,7 +308,8 @@ struct EngineT final : Engine {
     FusedArgs<real> fused_args(int64_t begin, int64_t end) const {
         FusedArgs<real> a;
         a.P = P;
-        a.pdf_in = pdf[cur].p; a.pdf_out = pdf[cur ^ 1].p;
+        a.pdf_in = pdf[cur].p; a.pdf_out = pdf[nxt()].p;
+        a.list = nullptr; a.list_n = 0;
         a.ccode = ccode.p; a.ccoef = ccoef.p; a.cface = cface.p; a.fcoef = fcoef.p;
         a.G.bf_na = bf_na.p; a.G.bf_nb = bf_nb.p; a.G.bf_ratio = bf_ratio.p;
         a.G.npdf = npdf.p; a.G.NTpad = plan.NTpad;
@@ -393,13 +412,13 @@ struct EngineT final : Engine {
         if ((rc = launch_nodes())) return rc;
         if ((rc = launch_faces(pdf[cur].p))) return rc;
         k_s_cells<real, Q, K><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, pdf[cur].p, s_feq.p, s_flux.p, s_cface.p,
-                                                                            s_csign.p, ipos.p, plan.Npad, plan.No, pdf[cur ^ 1].p);
+                                                                            s_csign.p, ipos.p, plan.Npad, plan.No, pdf[nxt()].p);
         ++launches;
         CU_TRY(cudaGetLastError());
         if (plan.No < plan.N) {   // halo copies are refreshed by the caller; keep them readable in both buffers
             err = "staged mode does not support halo cells"; return FVDBM_ERR_STATE;
         }
-        cur ^= 1; ++steps;
+        prev = cur; cur = nxt(); ++steps;
         return FVDBM_OK;
     }
 
@@ -434,7 +453,7 @@ struct EngineT final : Engine {
         if (forked) CU_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
         forked = false;
         phase0_done = false;
-        cur ^= 1; ++steps;
+        prev = cur; cur = nxt(); ++steps;
         return FVDBM_OK;
     }
 
@@ -497,6 +516,71 @@ struct EngineT final : Engine {
         return FVDBM_OK;
     }
 
+    // ---- temporal blocking --------------------------------------------------------------------------
+    bool temporal_possible() const {
+        return mode == FVDBM_MODE_FUSED && plan.t2_ok && plan.No == plan.N && variant == FVDBM_VARIANT_DIRECT &&
+               layout == 0 && t2_smem > 0 && t2_smem <= max_smem;
+    }
+    int set_temporal(int on) {
+        if (!on) { temporal = 0; return FVDBM_OK; }
+        if (!temporal_possible()) { err = "temporal blocking needs the fused direct kernel on a single-GPU handle"; return FVDBM_ERR_STATE; }
+        if (nbuf == 2) {                       // third buffer, copy of nothing in particular: holes must be zero
+            CU_TRY(pdf[2].alloc(pdf[0].n));
+            CU_TRY(cudaMemsetAsync(pdf[2].p, 0, pdf[2].bytes(), stream));
+            nbuf = 3;
+        }
+        temporal = 1; graph_steps = 0; drop_graphs();
+        return FVDBM_OK;
+    }
+
+    // Two iterations A(t) -> C(t+2).  Side stream: k_fused2 over the tiles (cells at level >= 2).
+    // Main stream: nodes(A); level<=2 cells A->B (list + range); nodes(B); level<=1 cells B->C.
+    int superstep() {
+        const int A = cur, B = (cur + 1) % 3, C = (cur + 2) % 3;
+        const int64_t end = owned_end();
+        CU_TRY(cudaEventRecord(ev_fork, stream));
+        CU_TRY(cudaStreamWaitEvent(stream2, ev_fork, 0));
+        {
+            Fused2Args<real> t;
+            t.P = P; t.pdf_in = pdf[A].p; t.pdf_out = pdf[C].p; t.ccoef = ccoef.p;
+            t.t2_off = t2_off.p; t.t2_n1 = t2_n1.p; t.t2_pos = t2_pos.p; t.t2_loff = t2_loff.p; t.t2_lnbr = t2_lnbr.p;
+            t.s0_stride = s0_stride; t.s1_stride = s1_stride;
+            k_fused2<real, Q, K, SCHEME><<<(unsigned)plan.t2_tiles, 256, t2_smem, stream2>>>(t);
+            ++launches;
+            CU_TRY(cudaGetLastError());
+        }
+        CU_TRY(cudaEventRecord(ev_join, stream2));
+        int rc;
+        auto thin = [&](int in, int out, bool with_list) -> int {
+            cur = in;                                            // node kernel + fused_args read pdf[cur]
+            int r = launch_nodes();
+            if (r) return r;
+            if (with_list && l2_list.n) {
+                FusedArgs<real> a = fused_args(0, 0);
+                a.pdf_out = pdf[out].p; a.list = l2_list.p; a.list_n = (int64_t)l2_list.n; a.reverse = 0;
+                k_fused_direct<real, Q, K, SCHEME, 0><<<blocks_for((int64_t)l2_list.n, 256), 256, 0, stream>>>(a);
+                ++launches;
+                CU_TRY(cudaGetLastError());
+            }
+            if (end > plan.D1start) {
+                FusedArgs<real> a = fused_args(plan.D1start, end);
+                a.pdf_out = pdf[out].p; a.reverse = 0;
+                k_fused_direct<real, Q, K, SCHEME, 0><<<blocks_for(end - plan.D1start, 256), 256, 0, stream>>>(a);
+                ++launches;
+                CU_TRY(cudaGetLastError());
+            }
+            return FVDBM_OK;
+        };
+        rc = thin(A, B, true);
+        if (!rc) rc = thin(B, C, false);
+        cur = A;
+        if (rc) return rc;
+        CU_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
+        prev = B;                  // only valid near the boundary: step() always finishes with a single step
+        cur = C; steps += 2;
+        return FVDBM_OK;
+    }
+
     int step_once() { return mode == FVDBM_MODE_STAGED ? step_staged_once() : step_fused_once(); }
 
     int step_phase(int phase) override {
@@ -532,8 +616,14 @@ struct EngineT final : Engine {
         CU_TRY(cudaSetDevice(device));
         int rc;
         if (mode == FVDBM_MODE_STAGED && (rc = ensure_staged_buffers())) return rc;
+        // temporal blocking: pairs of iterations, but the last iteration is always a single step so that
+        // the lagged observables (rho/vel/pdf_eq/flux of the previous populations) stay exact
+        while (temporal && n >= 3 && !phase0_done && !native_exchange()) {
+            if ((rc = superstep())) return rc;
+            n -= 2;
+        }
         while (n > 0) {
-            if (graph_steps > 0 && n >= graph_steps && !phase0_done && !native_exchange()) {   // NCCL ops stay out of graphs
+            if (graph_steps > 0 && nbuf == 2 && n >= graph_steps && !phase0_done && !native_exchange()) {   // NCCL ops stay out of graphs
                 auto it = graphs.find(cur);
                 if (it == graphs.end()) {
                     cudaGraphExec_t ge;
@@ -615,7 +705,7 @@ struct EngineT final : Engine {
             if (!expect_cells(Q)) return FVDBM_ERR_ARG;
             if (field == FVDBM_CELL_PDF_PREV && steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
             if ((rc = need_scratch((size_t)N * Q))) return rc;
-            const real* src = pdf[field == FVDBM_CELL_PDF ? cur : cur ^ 1].p;
+            const real* src = pdf[field == FVDBM_CELL_PDF ? cur : prev].p;
             k_export_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(src, pos.p, rows, scratch.p);
             ++launches;
             break;
@@ -626,7 +716,7 @@ struct EngineT final : Engine {
             if (steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
             if ((rc = need_scratch((size_t)N * per))) return rc;
             k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(
-                P, pdf[cur ^ 1].p, pos.p, rows, field == FVDBM_CELL_RHO ? scratch.p : nullptr,
+                P, pdf[prev].p, pos.p, rows, field == FVDBM_CELL_RHO ? scratch.p : nullptr,
                 field == FVDBM_CELL_VEL ? scratch.p : nullptr, field == FVDBM_CELL_PDF_EQ ? scratch.p : nullptr);
             ++launches;
             break;
@@ -635,7 +725,7 @@ struct EngineT final : Engine {
             if (!expect((size_t)F * Q)) return FVDBM_ERR_ARG;
             if (steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
             if ((rc = ensure_staged_buffers())) return rc;
-            if (mode != FVDBM_MODE_STAGED && (rc = launch_faces(pdf[cur ^ 1].p))) return rc;
+            if (mode != FVDBM_MODE_STAGED && (rc = launch_faces(pdf[prev].p))) return rc;
             CU_TRY(cudaMemcpyAsync(dst, s_flux.p, bytes, cudaMemcpyDeviceToHost, stream));
             CU_TRY(cudaStreamSynchronize(stream));
             return FVDBM_OK;
@@ -726,6 +816,7 @@ struct EngineT final : Engine {
         case FVDBM_OPT_GRAPH_STEPS: graph_steps = (int)v; break;
         case FVDBM_OPT_CTAS_PER_SM: ctas_per_sm = (int)v; break;
         case FVDBM_OPT_REVERSE_SWEEP: reverse_sweep = v ? 1 : 0; break;
+        case FVDBM_OPT_TEMPORAL: { int rc2 = set_temporal((int)v); if (rc2) return rc2; break; }
         default: err = "unknown option"; return FVDBM_ERR_ARG;
         }
         occ_cache = 0;
@@ -832,7 +923,7 @@ int64_t plan_array(const Plan<real>& p, const std::string& k, const void** ptr, 
 #define I32(name) if (k == #name) { *ptr = p.name.data(); *eb = 4; return (int64_t)p.name.size(); }
 #define REAL(name) if (k == #name) { *ptr = p.name.data(); *eb = (int32_t)sizeof(real); return (int64_t)p.name.size(); }
     I32(pos) I32(ipos) I32(ccode) I32(cface) I32(bf_na) I32(bf_nb) I32(tn_orig) I32(tn_type) I32(node_track)
-    I32(bt_off) I32(bt_nodes) I32(bf_la) I32(bf_lb) I32(ring_off) I32(ring_cell) I32(s_cface) I32(s_csign) I32(s_fcell) I32(s_fnode)
+    I32(t2_off) I32(t2_n1) I32(t2_pos) I32(l2_list) I32(bt_off) I32(bt_nodes) I32(bf_la) I32(bf_lb) I32(ring_off) I32(ring_cell) I32(s_cface) I32(s_csign) I32(s_fcell) I32(s_fnode)
     REAL(ccoef) REAL(fcoef) REAL(bf_ratio) REAL(ring_w) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel)
 #undef I32
 #undef REAL
@@ -842,7 +933,9 @@ template <typename real>
 int64_t plan_scalar(const Plan<real>& p, const std::string& k) {
     if (k == "N") return p.N; if (k == "F") return p.F; if (k == "P") return p.P; if (k == "No") return p.No;
     if (k == "Npad") return p.Npad; if (k == "Bstart") return p.Bstart; if (k == "Oend") return p.Oend;
-    if (k == "Hstart") return p.Hstart; if (k == "NB") return p.NB; if (k == "NT") return p.NT;
+    if (k == "Hstart") return p.Hstart; if (k == "D1start") return p.D1start;
+    if (k == "t2_tiles") return p.t2_tiles; if (k == "t2_max_entries") return p.t2_max_entries;
+    if (k == "t2_max_n01") return p.t2_max_n01; if (k == "t2_ok") return p.t2_ok ? 1 : 0; if (k == "NB") return p.NB; if (k == "NT") return p.NT;
     if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "NF") return p.NF; if (k == "NO") return p.NO;
     if (k == "max_tile_nodes") return p.max_tile_nodes; if (k == "NC") return p.NC;
     if (k == "fused_ok") return p.fused_ok ? 1 : 0;

@@ -23,6 +23,8 @@ struct FusedArgs {
     GhostTables<real> G;               // boundary sides + tracked node populations
     int64_t cell_begin, cell_end;      // position range, multiples of the CTA tile
     int reverse;                       // 1: sweep tiles from the top (L2 reuse of last step's writes)
+    const int32_t* __restrict__ list;  // optional explicit position list (direct kernel): cell = list[i]
+    int64_t list_n;
 };
 
 // ---- build-time tuning knobs (A/B'd on B200, see profiles/) -----------------------------------
@@ -87,8 +89,12 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     constexpr int NC = SCHEME == 0 ? 2 : 4;
     const int64_t nblk = gridDim.x;
     const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
-    const int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
-    if (c >= a.cell_end) return;
+    int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
+    if (a.list != nullptr) {                       // thin, list-driven pass (temporal schedule: level-2 cells)
+        const int64_t i = blk * blockDim.x + threadIdx.x;
+        if (i >= a.list_n) return;
+        c = a.list[i];
+    } else if (c >= a.cell_end) return;
     const size_t tile = (size_t)(c >> 5);
     const int lane = (int)(c & 31);
     const int32_t* gc = a.ccode + tile * (K * kTW) + lane;
@@ -253,6 +259,103 @@ __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, cons
             for (int q = 0; q < Q; ++q) go[q * kTW] = out[q];
         }
         __syncthreads();      // stage s may be refilled by the next iteration's issue
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Temporal blocking: TWO iterations per pass.  One CTA per tile of 256 cells at level >= 2 (no ghost
+// sides within two rings).  Phase 0 stages the time-t populations of the tile, its face-neighbour
+// ring and that ring's ring in shared memory; phase 1 advances tile + ring 1 to t+1 in shared memory
+// (ring 1 redundantly -- the neighbouring tiles compute the same bits); phase 2 advances the tile to
+// t+2 and writes it out.  Per cell and iteration the arithmetic is exactly advance_cell(), so the
+// result is bit-identical to two single steps, while DRAM sees one read + one write of the
+// populations and one read of the side coefficients per TWO iterations.
+// ------------------------------------------------------------------------------------------------
+template <typename real>
+struct Fused2Args {
+    Params<real> P;
+    const real* __restrict__ pdf_in;
+    real* __restrict__ pdf_out;
+    const real* __restrict__ ccoef;
+    const int32_t* __restrict__ t2_off;
+    const int32_t* __restrict__ t2_n1;
+    const int32_t* __restrict__ t2_pos;
+    const int64_t* __restrict__ t2_loff;
+    const uint16_t* __restrict__ t2_lnbr;
+    int s0_stride, s1_stride;              // shared-memory strides (entries) of the two staging arrays
+};
+
+template <typename real, int Q, int K, int SCHEME>
+__global__ void __launch_bounds__(256, (sizeof(real) == 4 ? 4 : 2)) k_fused2(const Fused2Args<real> a) {
+    constexpr int NC = SCHEME == 0 ? 2 : 4;
+    constexpr int T2 = 256;
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
+    real* s0 = reinterpret_cast<real*>(smem_raw2);
+    real* s1 = s0 + (size_t)Q * a.s0_stride;
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int64_t t0 = (int64_t)tile * T2;
+    const int off = a.t2_off[tile];
+    const int n12 = a.t2_off[tile + 1] - off, n1 = a.t2_n1[tile];
+    const int n01 = T2 + n1, nent = T2 + n12;
+    const int S0 = a.s0_stride, S1 = a.s1_stride;
+    const GhostTables<real> G0{nullptr, nullptr, nullptr, nullptr, 0};
+
+    // phase 0: stage populations at time t (own: coalesced; rings: gathers sorted by position)
+    for (int e = tid; e < nent; e += T2) {
+        const int64_t pc = e < T2 ? t0 + e : (int64_t)a.t2_pos[off + e - T2];
+        const real* src = a.pdf_in + pdf_index<Q>(pc);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) s0[q * S0 + e] = __ldg(src + q * kTW);
+    }
+    __syncthreads();
+
+    const uint16_t* lbase = a.t2_lnbr + (size_t)a.t2_loff[tile] * K;
+    int32_t code_own[K];
+    real coef_own[K * NC];
+    bool own_live = false;
+    // phase 1: tile + ring 1 -> t+1 (shared memory to shared memory)
+    for (int e = tid; e < n01; e += T2) {
+        int32_t code[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) code[k] = (int32_t)lbase[(size_t)e * K + k];
+        if (code[0] == 0xFFFF) continue;                       // padding position
+        const int64_t pc = e < T2 ? t0 + e : (int64_t)a.t2_pos[off + e - T2];
+        const real* gco = a.ccoef + (size_t)(pc >> 5) * (K * NC * kTW) + (pc & 31);
+        real coef[K * NC], f[Q], out[Q];
+#pragma unroll
+        for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) f[q] = s0[q * S0 + e];
+        auto load_nbr = [s0, S0](int64_t nb, real* fn) {
+#pragma unroll
+            for (int q = 1; q < Q; ++q) fn[q] = s0[q * S0 + (int)nb];
+        };
+        advance_cell<real, Q, K, SCHEME>(a.P, G0, f, code, coef, load_nbr, out);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) s1[q * S1 + e] = out[q];
+        if (e < T2) {                                          // keep the own cell's side records for phase 2
+            own_live = true;
+#pragma unroll
+            for (int k = 0; k < K; ++k) code_own[k] = code[k];
+#pragma unroll
+            for (int i = 0; i < K * NC; ++i) coef_own[i] = coef[i];
+        }
+    }
+    __syncthreads();
+
+    // phase 2: tile -> t+2
+    if (own_live) {
+        real f[Q], out[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) f[q] = s1[q * S1 + tid];
+        auto load_nbr = [s1, S1](int64_t nb, real* fn) {
+#pragma unroll
+            for (int q = 1; q < Q; ++q) fn[q] = s1[q * S1 + (int)nb];
+        };
+        advance_cell<real, Q, K, SCHEME>(a.P, G0, f, code_own, coef_own, load_nbr, out);
+        real* go = a.pdf_out + pdf_index<Q>(t0 + tid);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) go[q * kTW] = out[q];
     }
 }
 

@@ -40,7 +40,8 @@ template <typename real>
 struct Plan {
     int64_t N = 0, F = 0, P = 0, No = 0;
     int Q = 9, K = 3, M = 0, scheme = 0, NC = 2;
-    int64_t Npad = 0, Bstart = 0, Oend = 0, Hstart = 0;
+    int64_t Npad = 0, Bstart = 0, Oend = 0, Hstart = 0, D1start = 0;
+    std::vector<int32_t> l2_list;               // positions of the level-2 cells (inside the tiled group)
     std::vector<int32_t> pos, ipos;
     bool fused_ok = true;
     std::string why_not;
@@ -61,6 +62,76 @@ struct Plan {
     std::string error;
 
     bool fail(const std::string& msg) { error = msg; return false; }
+
+    // ---- temporal blocking (two iterations per pass) -------------------------------------------------
+    // Tiles of T2 consecutive positions over [0, D1start) (cells at level >= 2).  Entry list of a tile:
+    //   [ own (T2, implicit positions) | ring1 = face neighbours of own | ring2 = face neighbours of ring1 ]
+    // The kernel stages the time-t populations of all entries in shared memory, advances own+ring1 to
+    // t+1 there (ring1 redundantly: neighbouring tiles do the same, identically), then own to t+2.
+    // t2_lnbr[entry][k] = (local id of the side's other cell << 2) | (sign<0)<<1 | slot, 16 bit.
+    static constexpr int T2 = 256;
+    std::vector<int32_t> t2_off, t2_n1, t2_pos;     // per tile: offset into t2_pos, #ring1; ring positions
+    std::vector<int64_t> t2_loff;                   // per tile: offset (in entries) into t2_lnbr
+    std::vector<uint16_t> t2_lnbr;
+    int64_t t2_tiles = 0, t2_max_entries = 0, t2_max_n01 = 0;
+    bool t2_ok = false;
+
+    void build_temporal_tiles(const fvdbm_desc& d, const std::vector<int32_t>& other, const std::vector<uint8_t>& slot) {
+        t2_ok = false;
+        t2_tiles = D1start / T2;
+        if (t2_tiles == 0) return;
+        t2_off.assign(t2_tiles + 1, 0); t2_n1.assign(t2_tiles, 0); t2_loff.assign(t2_tiles + 1, 0);
+        t2_pos.clear(); t2_lnbr.clear();
+        std::vector<int32_t> stamp(Npad, -1), lid(Npad, 0);
+        std::vector<int32_t> ring;
+        for (int64_t t = 0; t < t2_tiles; ++t) {
+            const int64_t t0 = t * T2;
+            ring.clear();
+            for (int e = 0; e < T2; ++e) { stamp[t0 + e] = (int32_t)t; lid[t0 + e] = e; }
+            // collect a ring (unstamped face neighbours of the given entries), sort it by position so that
+            // consecutive threads gather consecutive positions (shared 32 B sectors), then assign local ids
+            auto grow = [&](int64_t from_begin, int64_t from_end, bool from_own) {
+                const size_t first = ring.size();
+                for (int64_t e = from_begin; e < from_end; ++e) {
+                    const int64_t pc = from_own ? t0 + e : ring[e];
+                    const int64_t c = ipos[pc];
+                    if (c < 0 || c >= No) continue;
+                    for (int k = 0; k < K; ++k) {
+                        const int32_t o = other[c * K + k];
+                        if (o < 0) continue;                    // cannot happen for level >= 1 cells
+                        const int64_t np = pos[o];
+                        if (stamp[np] != (int32_t)t) { stamp[np] = (int32_t)t; ring.push_back((int32_t)np); }
+                    }
+                }
+                std::sort(ring.begin() + first, ring.end());
+                for (size_t i = first; i < ring.size(); ++i) lid[ring[i]] = (int32_t)(T2 + i);
+            };
+            grow(0, T2, true);
+            const int64_t n1 = (int64_t)ring.size();
+            grow(0, n1, false);
+            const int64_t n2 = (int64_t)ring.size() - n1;
+            t2_n1[t] = (int32_t)n1;
+            t2_off[t + 1] = t2_off[t] + (int32_t)ring.size();
+            t2_pos.insert(t2_pos.end(), ring.begin(), ring.end());
+            t2_loff[t + 1] = t2_loff[t] + (T2 + n1);
+            for (int64_t e = 0; e < T2 + n1; ++e) {
+                const int64_t pc = e < T2 ? t0 + e : ring[e - T2];
+                const int64_t c = ipos[pc];
+                for (int k = 0; k < K; ++k) {
+                    uint16_t v = 0xFFFF;                        // hole (padding position): skipped by the kernel
+                    if (c >= 0 && c < No) {
+                        const int32_t o = other[c * K + k];
+                        const int neg = d.cell_face_sign[c * K + k] < 0 ? 1 : 0;
+                        v = (uint16_t)((lid[pos[o]] << 2) | (neg << 1) | slot[c * K + k]);
+                    }
+                    t2_lnbr.push_back(v);
+                }
+            }
+            t2_max_entries = std::max<int64_t>(t2_max_entries, T2 + n1 + n2);
+            t2_max_n01 = std::max<int64_t>(t2_max_n01, T2 + n1);
+        }
+        t2_ok = t2_max_entries < (1 << 14);
+    }
 
     bool build(const fvdbm_desc& d) {
         N = d.N; F = d.F; P = d.P; Q = d.Q; K = d.K; M = d.M; scheme = d.scheme;
@@ -128,15 +199,34 @@ struct Plan {
             // interior = owned cells whose K sides are all interior faces to owned cells: they need neither
             // node values nor halo copies, so the engine updates them concurrently with the exchange /
             // node kernel / border update (api.cu: step_fused_once).
-            std::vector<uint8_t> border(N, 0);
+            // level = face-graph distance to the nearest border cell, capped at 3.  Positions are grouped
+            // [level>=2 | level 1 | level 0 = border]: the single-step schedule uses interior = [0,Bstart);
+            // the two-step temporal schedule tiles [0,D1start) and runs thin single-step passes over
+            // [D1start,end) plus the explicit list of level-2 cells (l2_list), which stay in locality order
+            // inside the tiled group so that no tile is a thin strip with a huge ring.
+            std::vector<uint8_t> lvl(N, 3);
             for (int64_t c = 0; c < No; ++c)
                 for (int k = 0; k < K; ++k) {
                     int32_t o = other[c * K + k];
-                    if (o == -1 || o >= No) border[c] = 1;
+                    if (o == -1 || o >= No) lvl[c] = 0;
                 }
-            for (int64_t r = 0; r < No; ++r) if (!border[order[r]]) pos[order[r]] = (int32_t)p++;
+            for (int L = 0; L < 2; ++L)
+                for (int64_t c = 0; c < No; ++c)
+                    if (lvl[c] == L)
+                        for (int k = 0; k < K; ++k) {
+                            int32_t o = other[c * K + k];
+                            if (o >= 0 && o < No && lvl[o] > L + 1) lvl[o] = (uint8_t)(L + 1);
+                        }
+            l2_list.clear();
+            for (int64_t r = 0; r < No; ++r)
+                if (lvl[order[r]] >= 2) {
+                    if (lvl[order[r]] == 2) l2_list.push_back((int32_t)p);
+                    pos[order[r]] = (int32_t)p++;
+                }
+            D1start = round_up(p, PAD_TO); p = D1start;
+            for (int64_t r = 0; r < No; ++r) if (lvl[order[r]] == 1) pos[order[r]] = (int32_t)p++;
             Bstart = round_up(p, PAD_TO); p = Bstart;
-            for (int64_t r = 0; r < No; ++r) if (border[order[r]]) pos[order[r]] = (int32_t)p++;
+            for (int64_t r = 0; r < No; ++r) if (lvl[order[r]] == 0) pos[order[r]] = (int32_t)p++;
             Oend = p; Hstart = round_up(p, PAD_TO); p = Hstart;
             for (int64_t r = No; r < N; ++r) pos[order[r]] = (int32_t)p++;
         } else {
@@ -301,6 +391,7 @@ struct Plan {
             while (cur_bt < nbt) { ++cur_bt; bt_off[cur_bt] = (int32_t)bt_nodes.size(); }
             for (int64_t t = 0; t < nbt; ++t) max_tile_nodes = std::max<int64_t>(max_tile_nodes, bt_off[t + 1] - bt_off[t]);
             if (NB >= (int64_t(1) << 28)) return fail("too many boundary sides");
+            if (!has_halo) build_temporal_tiles(d, other, slot);
         }
         return true;
     }

@@ -92,7 +92,10 @@ enum fvdbm_option {
     FVDBM_OPT_STAGES = 2,         /* TMA variant: pipeline depth (2..4)                      */
     FVDBM_OPT_GRAPH_STEPS = 3,    /* steps captured per CUDA graph (0 = no graph)            */
     FVDBM_OPT_CTAS_PER_SM = 4,    /* persistent grid = 148 * this (0 = occupancy query)      */
-    FVDBM_OPT_REVERSE_SWEEP = 5   /* 1: odd steps sweep tiles backwards (L2 reuse of writes) */
+    FVDBM_OPT_REVERSE_SWEEP = 5,  /* 1: odd steps sweep tiles backwards (L2 reuse of writes) */
+    FVDBM_OPT_TEMPORAL = 6        /* 1: temporal blocking -- two iterations per pass over overlapped tiles
+                                     (bit-identical results, about half the DRAM traffic per iteration);
+                                     single-GPU fused handles only */
 };
 
 typedef struct fvdbm_handle fvdbm_handle;
