@@ -365,6 +365,13 @@ class Environment:
         except Exception:
             pass
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def __getstate__(self):
         """Pickle = download (reference Mesher.to_pickle dumps (env, mesher), mesher.py:600-602)."""
         c, f, n = self.cells._src, self.faces._src, self.nodes._src
