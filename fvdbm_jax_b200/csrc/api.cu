@@ -141,7 +141,6 @@ struct EngineT final : Engine {
     DevBuf<int64_t> t2_loff;
     DevBuf<uint16_t> t2_lnbr;
     size_t t2_smem = 0;
-    int t2_threads = 256;                // CTA size of k_fused2 (256 own cells + extra warps for the ring entries)
     int nxt() const { return (cur + 1) % nbuf; }
     DevBuf<int32_t> ccode, bf_na, bf_nb, pos, ipos, ring_off, ring_cell, tn_type;
     DevBuf<real> ccoef, fcoef, bf_ratio, ring_w, npdf, nrho, nvel;
@@ -282,7 +281,6 @@ struct EngineT final : Engine {
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
-        if (const char* e = getenv("FVDBM_T2_THREADS")) { int v = atoi(e); if (v >= 256 && v <= 384 && v % 32 == 0) t2_threads = v; }
         if (const char* e = getenv("FVDBM_TEMPORAL")) { int rc2 = set_temporal(atoi(e)); if (rc2) return rc2; }
         if (variant == FVDBM_VARIANT_AUTO) variant = FVDBM_VARIANT_DIRECT;
         return sanitize_options();
@@ -547,7 +545,7 @@ struct EngineT final : Engine {
             t.P = P; t.pdf_in = pdf[A].p; t.pdf_out = pdf[C].p; t.ccoef = ccoef.p;
             t.t2_off = t2_off.p; t.t2_n1 = t2_n1.p; t.t2_pos = t2_pos.p; t.t2_loff = t2_loff.p; t.t2_lnbr = t2_lnbr.p;
             t.s0_stride = s0_stride; t.s1_stride = s1_stride;
-            k_fused2<real, Q, K, SCHEME><<<(unsigned)plan.t2_tiles, t2_threads, t2_smem, stream2>>>(t);
+            k_fused2<real, Q, K, SCHEME><<<(unsigned)plan.t2_tiles, 256, t2_smem, stream2>>>(t);
             ++launches;
             CU_TRY(cudaGetLastError());
         }

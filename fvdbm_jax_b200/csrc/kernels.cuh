@@ -286,14 +286,13 @@ struct Fused2Args {
 };
 
 template <typename real, int Q, int K, int SCHEME>
-__global__ void __launch_bounds__(384, (sizeof(real) == 4 ? 3 : 1)) k_fused2(const Fused2Args<real> a) {
+__global__ void __launch_bounds__(256, (sizeof(real) == 4 ? 4 : 2)) k_fused2(const Fused2Args<real> a) {
     constexpr int NC = SCHEME == 0 ? 2 : 4;
     constexpr int T2 = 256;
     extern __shared__ __align__(16) unsigned char smem_raw2[];
     real* s0 = reinterpret_cast<real*>(smem_raw2);
     real* s1 = s0 + (size_t)Q * a.s0_stride;
-    // blockDim.x >= T2: the extra warps take the ring entries so that phases 0/1 finish in one round
-    const int tile = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const int tile = blockIdx.x, tid = threadIdx.x;
     const int64_t t0 = (int64_t)tile * T2;
     const int off = a.t2_off[tile];
     const int n12 = a.t2_off[tile + 1] - off, n1 = a.t2_n1[tile];
@@ -302,7 +301,7 @@ __global__ void __launch_bounds__(384, (sizeof(real) == 4 ? 3 : 1)) k_fused2(con
     const GhostTables<real> G0{nullptr, nullptr, nullptr, nullptr, 0};
 
     // phase 0: stage populations at time t (own: coalesced; rings: gathers sorted by position)
-    for (int e = tid; e < nent; e += NT) {
+    for (int e = tid; e < nent; e += T2) {
         const int64_t pc = e < T2 ? t0 + e : (int64_t)a.t2_pos[off + e - T2];
         const real* src = a.pdf_in + pdf_index<Q>(pc);
 #pragma unroll
@@ -315,7 +314,7 @@ __global__ void __launch_bounds__(384, (sizeof(real) == 4 ? 3 : 1)) k_fused2(con
     real coef_own[K * NC];
     bool own_live = false;
     // phase 1: tile + ring 1 -> t+1 (shared memory to shared memory)
-    for (int e = tid; e < n01; e += NT) {
+    for (int e = tid; e < n01; e += T2) {
         int32_t code[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) code[k] = (int32_t)lbase[(size_t)e * K + k];
