@@ -109,7 +109,8 @@ def measured_peak():
 
 def cpu_baseline(scheme, seconds=12.0, nx=1000):
     """Oracle C/OpenMP port on the host cores over a bounded sample of the same mesh family."""
-    from oracle.step_c import COracle, threads
+    from oracle.step_c import COracle, threads, use_all_cores
+    use_all_cores()
     m, dyn, cells, faces, nodes, _ = build_problem(nx, nx, scheme)
     static, state = static_state(cells, faces, nodes)
     o = COracle(static, state, 9, dyn.tau, dyn.delta_t, scheme, np.float32)
@@ -128,7 +129,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.step_c import COracle, threads
+    from oracle.step_c import COracle, threads, use_all_cores
+    use_all_cores()
     nx = args.ref_nx
     m, dyn, cells, faces, nodes, _ = build_problem(nx, nx, args.scheme)
     static, state = static_state(cells, faces, nodes)

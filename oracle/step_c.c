@@ -80,6 +80,15 @@ int fvdbm_oracle_step_f64(const oracle_desc* d, double* pdf, double* rho, double
     return -1;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host thread it can get */
+void fvdbm_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int fvdbm_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -23,6 +23,13 @@ def threads() -> int:
     return int(C.CDLL(LIB).fvdbm_oracle_threads())
 
 
+def use_all_cores() -> int:
+    """Ignore an inherited OMP_NUM_THREADS=1 (torchrun sets it) and use every host core."""
+    lib = C.CDLL(LIB)
+    lib.fvdbm_oracle_set_threads(C.c_int(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+    return int(lib.fvdbm_oracle_threads())
+
+
 class COracle:
     """Same constructor contract as oracle.step_numpy.StepOracle."""
 
