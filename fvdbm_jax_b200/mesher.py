@@ -284,6 +284,15 @@ class Mesher:
         nodes.rho[m] = rho
         return nodes
 
+    # ------------------------------------------------------------------ decomposition
+    def partition(self, nparts: int, method: str = "auto", refine: bool = True):
+        """Owner rank of every cell for a multi-GPU run (north_star: "the Mesher partitions cells ...
+        across the 8 B200s"): locality chunks of the cell graph + METIS-style boundary refinement.
+        See fvdbm_jax_b200.partition / .distributed for local meshes, halos and the exchange."""
+        from .partition import partition_cells
+        return partition_cells(np.asarray(self.face_cell_indices), self.cells.shape[0], nparts,
+                               centers=self.cell_centers, method=method, refine=refine)
+
     # ------------------------------------------------------------------ export
     def to_vtk(self, env: Environment, filename: str, save_f: bool = False, save_feq: bool = False):
         """Legacy-VTK writer with the cell data of reference mesher.py:562-598 (no pyvista)."""

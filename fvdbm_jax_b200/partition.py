@@ -25,7 +25,8 @@ import numpy as np
 
 from .reorder import hilbert_index, hilbert_perm, order_to_perm
 
-__all__ = ["GlobalMesh", "LocalMesh", "partition_sfc", "partition_strips", "refine_partition",
+__all__ = ["GlobalMesh", "LocalMesh", "partition_sfc", "partition_strips", "partition_rcm", "partition_cells",
+           "refine_partition",
            "extract_local", "exchange_lists", "edge_cut"]
 
 
@@ -96,6 +97,34 @@ def partition_strips(centers: np.ndarray, nparts: int, axis: int = 1) -> np.ndar
     order = np.argsort(centers[:, axis], kind="stable")
     part = np.empty(n, dtype=np.int32)
     part[order] = (np.arange(n, dtype=np.int64) * nparts // n).astype(np.int32)
+    return part
+
+
+def partition_rcm(stencil: np.ndarray, n_cells: int, nparts: int) -> np.ndarray:
+    """Graph-only partitioning (no coordinates needed): balanced chunks of the reverse Cuthill-McKee
+    ordering, i.e. contiguous bands of BFS levels of the cell adjacency graph."""
+    from .reorder import rcm_perm
+    perm = rcm_perm(stencil, n_cells)
+    return (perm.astype(np.int64) * nparts // n_cells).astype(np.int32)
+
+
+def partition_cells(stencil: np.ndarray, n_cells: int, nparts: int, centers=None, method: str = "auto",
+                    refine: bool = True) -> np.ndarray:
+    """Front door: 'sfc' (Hilbert chunks, needs centroids), 'rcm' (graph only), 'strips', or 'auto'
+    (sfc when centroids are known, else rcm); optionally followed by the METIS-style greedy
+    boundary refinement (edge-cut reduction under a 3 % balance constraint)."""
+    if method == "auto":
+        method = "sfc" if centers is not None else "rcm"
+    if method == "sfc":
+        part = partition_sfc(np.asarray(centers), nparts)
+    elif method == "strips":
+        part = partition_strips(np.asarray(centers), nparts)
+    elif method == "rcm":
+        part = partition_rcm(stencil, n_cells, nparts)
+    else:
+        raise ValueError(f"unknown partition method {method!r}")
+    if refine and nparts > 1:
+        part = refine_partition(stencil, part, nparts)
     return part
 
 

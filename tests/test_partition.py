@@ -155,3 +155,18 @@ def test_strip_window_is_bitwise_window_of_whole_mesh():
     cg = {int(g): i for i, g in enumerate(whole.cell_gid)}
     for lc, g in enumerate(win.cell_gid):
         assert np.array_equal(whole.point_gid[whole.elements[cg[int(g)]]], win.point_gid[win.elements[lc]])
+
+
+@pytest.mark.parametrize("method", ["sfc", "rcm", "strips", "auto"])
+def test_mesher_partition_front_door(method):
+    m, dyn, g = problem(nx=36, ny=30)
+    part = m.partition(4, method=method)
+    sizes = np.bincount(part, minlength=4)
+    assert part.shape == (g.num_cells,) and sizes.min() > 0 and sizes.max() <= 1.04 * g.num_cells / 4 + 2
+    # far better than a random assignment, and every part is usable by extract_local
+    rnd = np.random.default_rng(0).integers(0, 4, g.num_cells)
+    assert edge_cut(g.stencil, part) * 8 < edge_cut(g.stencil, rnd)
+    for r in range(4):
+        assert extract_local(g, part, r).n_owned == sizes[r]
+    with pytest.raises(ValueError):
+        m.partition(4, method="metis5")
