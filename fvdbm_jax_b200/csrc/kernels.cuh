@@ -31,6 +31,9 @@ struct FusedArgs {
 #ifndef FVDBM_DIRECT_MINCTAS
 #define FVDBM_DIRECT_MINCTAS 0        // >0: __launch_bounds__(256, N) for the direct kernel
 #endif
+#ifndef FVDBM_PREFETCH_NBR
+#define FVDBM_PREFETCH_NBR 0          // 1: prefetch.global.L1 the neighbour populations of sides 1..K-1 up front
+#endif
 #ifndef FVDBM_STREAM_HINTS
 #define FVDBM_STREAM_HINTS 0          // 1: ld.global.cs for the never-reused side records, st.global.cs for stores
 #endif
@@ -97,26 +100,42 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     } else if (c >= a.cell_end) return;
     const size_t tile = (size_t)(c >> 5);
     const int lane = (int)(c & 31);
+    // Issue every independent streaming load (side codes, side coefficients, own populations) BEFORE the
+    // first use of any of them: the ncu source view showed ~30 % of the stall samples on the hole test of
+    // code[0], i.e. a full memory round trip spent before the other loads were even in flight.  An early
+    // `return` would let ptxas sink the loads below it again, so padding positions are not skipped: they
+    // run the (in-bounds, harmless) arithmetic on a neutral code and only their stores are suppressed.
     const int32_t* gc = a.ccode + tile * (K * kTW) + lane;
     int32_t code[K];
-    code[0] = ld_static(gc);
-    if (code[0] == kHole) return;
 #pragma unroll
-    for (int k = 1; k < K; ++k) code[k] = ld_static(gc + k * kTW);
+    for (int k = 0; k < K; ++k) code[k] = ld_static(gc + k * kTW);
     real coef[K * NC];
     if (LAYOUT == 0) {
         const real* gco = a.ccoef + tile * (K * NC * kTW) + lane;
 #pragma unroll
         for (int i = 0; i < K * NC; ++i) coef[i] = ld_static(gco + i * kTW);
-    } else {
-        const int32_t* gf = a.cface + tile * (K * kTW) + lane;
-#pragma unroll
-        for (int k = 0; k < K; ++k) load_face_record<real, NC>(a.fcoef, ld_static(gf + k * kTW), coef + k * NC);
     }
     const real* gp = a.pdf_in + tile * (Q * kTW) + lane;
     real f[Q], out[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) f[q] = __ldg(gp + q * kTW);
+    const bool live = code[0] != kHole;
+    if (!live) code[0] = 0;                        // neutral: interior side towards position 0
+    if (LAYOUT != 0) {
+        const int32_t* gf = a.cface + tile * (K * kTW) + lane;
+#pragma unroll
+        for (int k = 0; k < K; ++k) load_face_record<real, NC>(a.fcoef, ld_static(gf + k * kTW), coef + k * NC);
+    }
+#if FVDBM_PREFETCH_NBR
+    // pull the neighbours' lines towards L1 while side 0 is being computed (no registers held)
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+        if (code[k] >= 0) {
+            const real* pn = a.pdf_in + pdf_index<Q>((int64_t)(code[k] >> 2));
+#pragma unroll
+            for (int q = 1; q < Q; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + q * kTW));
+        }
+#endif
     const real* pin = a.pdf_in;
     auto load_nbr = [pin](int64_t nb, real* fn) {
         const real* pn = pin + pdf_index<Q>(nb);
@@ -125,8 +144,10 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     };
     advance_cell<real, Q, K, SCHEME>(a.P, a.G, f, code, coef, load_nbr, out);
     real* go = a.pdf_out + tile * (Q * kTW) + lane;
+    if (live) {
 #pragma unroll
-    for (int q = 0; q < Q; ++q) st_result(go + q * kTW, out[q]);
+        for (int q = 0; q < Q; ++q) st_result(go + q * kTW, out[q]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
