@@ -411,6 +411,10 @@ template <typename real, int Q>
 __device__ __forceinline__ void warp_eval_node(const NodeArgs<real>& a, int node, int lane, real& rho_n, real& ux_n, real& uy_n,
                                                real* pdf_n) {
     const int beg = a.ring_off[node], end = a.ring_off[node + 1];
+    // prescribed values / type are independent of the ring: issue their loads up front so they overlap
+    // the ring gathers instead of adding a dependent memory round trip after the reduction
+    const int type = a.tn_type[node];
+    rho_n = a.nrho[node]; ux_n = a.nvel[node]; uy_n = a.nvel[a.NTpad + node];
     real sw = real(0), srho = real(0), sux = real(0), suy = real(0);
     real sneq[Q];
 #pragma unroll
@@ -427,8 +431,7 @@ __device__ __forceinline__ void warp_eval_node(const NodeArgs<real>& a, int node
     sw = warp_sum(sw); srho = warp_sum(srho); sux = warp_sum(sux); suy = warp_sum(suy);
 #pragma unroll
     for (int q = 0; q < Q; ++q) sneq[q] = warp_sum(sneq[q]);
-    rho_n = a.nrho[node]; ux_n = a.nvel[node]; uy_n = a.nvel[a.NTpad + node];
-    node_finish<real, Q>(a.P, a.tn_type[node], sw, srho, sux, suy, sneq, rho_n, ux_n, uy_n, pdf_n);
+    node_finish<real, Q>(a.P, type, sw, srho, sux, suy, sneq, rho_n, ux_n, uy_n, pdf_n);
 }
 
 template <typename real, int Q>
