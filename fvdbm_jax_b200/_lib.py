@@ -234,5 +234,5 @@ class HostPlan:
             pass
 
 
-_PLAN_I32 = {"t2_off", "t2_n1", "t2_pos", "l2_list", "pos", "ipos", "ccode", "cface", "bt_off", "bt_nodes", "bf_la", "bf_lb", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
+_PLAN_I32 = {"ring_fcell", "t2_off", "t2_n1", "t2_pos", "l2_list", "pos", "ipos", "ccode", "cface", "bt_off", "bt_nodes", "bf_la", "bf_lb", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
              "ring_cell", "s_cface", "s_csign", "s_fcell", "s_fnode"}

@@ -247,9 +247,8 @@ struct EngineT final : Engine {
             CU_TRY(cudaFuncSetAttribute(k_border<real, Q, K, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)prop.sharedMemPerBlockOptin));
         }
-        CU_TRY(ring_off.upload(plan.ring_off, stream));
-        CU_TRY(ring_cell.upload(plan.ring_cell, stream));
-        CU_TRY(ring_w.upload(plan.ring_w, stream));
+        CU_TRY(ring_cell.upload(plan.ring_fcell, stream));     // fixed-width ring table [NA][MR]
+        CU_TRY(ring_w.upload(plan.ring_fw, stream));
         CU_TRY(tn_type.upload(plan.tn_type, stream));
         CU_TRY(npdf.upload(plan.tn_pdf, stream));
         CU_TRY(nrho.upload(plan.tn_rho, stream));
@@ -264,7 +263,7 @@ struct EngineT final : Engine {
         CU_TRY(cudaStreamSynchronize(stream));
         // host staging vectors are no longer needed
         plan.ccode = {}; plan.ccoef = {}; plan.cface = {}; plan.fcoef = {}; plan.s_cface = {}; plan.s_csign = {}; plan.s_fcell = {}; plan.s_fnode = {};
-        plan.ring_cell = {}; plan.ring_w = {}; plan.tn_pdf = {}; plan.t2_pos = {}; plan.t2_lnbr = {}; plan.bt_nodes = {}; plan.bf_la = {}; plan.bf_lb = {};
+        plan.ring_cell = {}; plan.ring_w = {}; plan.ring_fcell = {}; plan.ring_fw = {}; plan.tn_pdf = {}; plan.t2_pos = {}; plan.t2_lnbr = {}; plan.bt_nodes = {}; plan.bf_la = {}; plan.bf_lb = {};
         int rc = set(FVDBM_CELL_PDF, d.cell_pdf, (size_t)plan.N * Q * sizeof(real));
         if (rc) return rc;
         // opt-in shared memory for the TMA kernel
@@ -321,7 +320,7 @@ struct EngineT final : Engine {
     NodeArgs<real> node_args(int64_t count) const {
         NodeArgs<real> a;
         a.P = P; a.pdf = pdf[cur].p;
-        a.ring_off = ring_off.p; a.ring_cell = ring_cell.p; a.ring_w = ring_w.p; a.tn_type = tn_type.p;
+        a.ring_cell = ring_cell.p; a.ring_w = ring_w.p; a.MR = (int)plan.MR; a.tn_type = tn_type.p;
         a.npdf = npdf.p; a.nrho = nrho.p; a.nvel = nvel.p; a.NTpad = plan.NTpad; a.NA = (int)count;
         return a;
     }
@@ -924,7 +923,7 @@ int64_t plan_array(const Plan<real>& p, const std::string& k, const void** ptr, 
 #define REAL(name) if (k == #name) { *ptr = p.name.data(); *eb = (int32_t)sizeof(real); return (int64_t)p.name.size(); }
     I32(pos) I32(ipos) I32(ccode) I32(cface) I32(bf_na) I32(bf_nb) I32(tn_orig) I32(tn_type) I32(node_track)
     I32(t2_off) I32(t2_n1) I32(t2_pos) I32(l2_list) I32(bt_off) I32(bt_nodes) I32(bf_la) I32(bf_lb) I32(ring_off) I32(ring_cell) I32(s_cface) I32(s_csign) I32(s_fcell) I32(s_fnode)
-    REAL(ccoef) REAL(fcoef) REAL(bf_ratio) REAL(ring_w) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel)
+    REAL(ccoef) REAL(fcoef) REAL(bf_ratio) REAL(ring_w) REAL(ring_fw) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel)
 #undef I32
 #undef REAL
     return -1;
@@ -936,7 +935,7 @@ int64_t plan_scalar(const Plan<real>& p, const std::string& k) {
     if (k == "Hstart") return p.Hstart; if (k == "D1start") return p.D1start;
     if (k == "t2_tiles") return p.t2_tiles; if (k == "t2_max_entries") return p.t2_max_entries;
     if (k == "t2_max_n01") return p.t2_max_n01; if (k == "t2_ok") return p.t2_ok ? 1 : 0; if (k == "NB") return p.NB; if (k == "NT") return p.NT;
-    if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "NF") return p.NF; if (k == "NO") return p.NO;
+    if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "NF") return p.NF; if (k == "NO") return p.NO; if (k == "MR") return p.MR;
     if (k == "max_tile_nodes") return p.max_tile_nodes; if (k == "NC") return p.NC;
     if (k == "fused_ok") return p.fused_ok ? 1 : 0;
     return -1;

@@ -387,9 +387,9 @@ template <typename real>
 struct NodeArgs {
     Params<real> P;
     const real* __restrict__ pdf;          // current populations (AoSoA)
-    const int32_t* __restrict__ ring_off;
-    const int32_t* __restrict__ ring_cell;
-    const real* __restrict__ ring_w;
+    const int32_t* __restrict__ ring_cell;  // fixed-width ring table [NA][MR] (plan.hpp: ring_fcell)
+    const real* __restrict__ ring_w;        //                               (ring_fw; 0 = unused slot)
+    int MR;
     const int32_t* __restrict__ tn_type;
     real* __restrict__ npdf;               // [Q][NTpad]
     real* __restrict__ nrho;               // [NTpad]
@@ -410,7 +410,6 @@ __device__ __forceinline__ real warp_sum(real v) {
 template <typename real, int Q>
 __device__ __forceinline__ void warp_eval_node(const NodeArgs<real>& a, int node, int lane, real& rho_n, real& ux_n, real& uy_n,
                                                real* pdf_n) {
-    const int beg = a.ring_off[node], end = a.ring_off[node + 1];
     // prescribed values / type are independent of the ring: issue their loads up front so they overlap
     // the ring gathers instead of adding a dependent memory round trip after the reduction
     const int type = a.tn_type[node];
@@ -419,14 +418,16 @@ __device__ __forceinline__ void warp_eval_node(const NodeArgs<real>& a, int node
     real sneq[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) sneq[q] = real(0);
-    for (int i = beg + lane; i < end; i += 32) {
-        const int64_t c = a.ring_cell[i];
+    for (int j = lane; j < a.MR; j += 32) {                 // lane j <-> ring slot j (same order as the CSR)
+        const size_t i = (size_t)node * a.MR + j;
         const real w = a.ring_w[i];
-        const real* p = a.pdf + pdf_index<Q>(c);
-        real f[Q];
+        if (w != real(0)) {
+            const real* p = a.pdf + pdf_index<Q>((int64_t)a.ring_cell[i]);
+            real f[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) f[q] = p[q * kTW];
-        node_accumulate<real, Q>(a.P, f, w, sw, srho, sux, suy, sneq);
+            for (int q = 0; q < Q; ++q) f[q] = p[q * kTW];
+            node_accumulate<real, Q>(a.P, f, w, sw, srho, sux, suy, sneq);
+        }
     }
     sw = warp_sum(sw); srho = warp_sum(srho); sux = warp_sum(sux); suy = warp_sum(suy);
 #pragma unroll

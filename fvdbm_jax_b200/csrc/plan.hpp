@@ -58,6 +58,11 @@ struct Plan {
     int64_t max_tile_nodes = 0;
     std::vector<int32_t> tn_orig, tn_type, node_track, tn_active, ring_off, ring_cell;
     std::vector<real> ring_w, tn_pdf, tn_rho, tn_vel;
+    // the same rings as a fixed-width table [NA][MR] (zero weight = unused slot): lets the node kernel index
+    // its ring entries directly instead of first loading CSR offsets (one dependent memory level less)
+    std::vector<int32_t> ring_fcell;
+    std::vector<real> ring_fw;
+    int64_t MR = 0;
     std::vector<int32_t> s_cface, s_csign, s_fcell, s_fnode;
     std::string error;
 
@@ -302,6 +307,16 @@ struct Plan {
             }
             ring_off[t + 1] = (int32_t)ring_cell.size();
         }
+
+        MR = 1;
+        for (int64_t t = 0; t < NA; ++t) MR = std::max<int64_t>(MR, ring_off[t + 1] - ring_off[t]);
+        ring_fcell.assign((size_t)std::max<int64_t>(NA, 1) * MR, 0);
+        ring_fw.assign((size_t)std::max<int64_t>(NA, 1) * MR, real(0));
+        for (int64_t t = 0; t < NA; ++t)
+            for (int i = ring_off[t]; i < ring_off[t + 1]; ++i) {
+                ring_fcell[(size_t)t * MR + (i - ring_off[t])] = ring_cell[i];
+                ring_fw[(size_t)t * MR + (i - ring_off[t])] = ring_w[i];
+            }
 
         // ---- staged statics (general path + observables) ---------------------------------------
         s_cface.assign((size_t)K * Npad, 0);
