@@ -56,6 +56,22 @@ def test_golden_all_fields(name, mode, dtype):
     env.close()
 
 
+@pytest.mark.parametrize("mode", ["direct", "tma", "staged"])
+@pytest.mark.parametrize("name", golden.names(fp32=True))
+def test_fp32_engine_vs_reference_run_in_fp32(name, mode):
+    """*_f32 fixtures = the reference's own code executed with every float in fp32 (what stock JAX
+    does, x64 off): the closest available stand-in for "the reference's JAX CPU path"; 1e-5 relative."""
+    case = golden.Case(name)
+    assert case.bits == 32
+    env = make_env(case, np.float32, mode)
+    done = 0
+    for s in case.steps:
+        env = env.step(s - done)
+        done = s
+        check_state(env, case, s, 1e-5)
+    env.close()
+
+
 def _square_problem(nx, ny, scheme="lax_wendroff", periodic=False, seed=11, perturb=True, lid=0.1):
     raw = meshgen.triangulated_square(nx, ny, seed=seed, periodic_x=periodic)
     m = fb.Mesher()
