@@ -107,21 +107,56 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(scheme, seconds=12.0, nx=1000):
-    """Oracle C/OpenMP port on the host cores over a bounded sample of the same mesh family."""
+def cpu_baseline(scheme, problem, seconds=12.0):
+    """Oracle C/OpenMP port on the host cores: a bounded number of iterations of the SAME mesh the GPU
+    arm ran (BASELINE.json configs[3] by default)."""
     from oracle.step_c import COracle, threads, use_all_cores
     use_all_cores()
-    m, dyn, cells, faces, nodes, _ = build_problem(nx, nx, scheme)
+    m, dyn, cells, faces, nodes = problem
     static, state = static_state(cells, faces, nodes)
     o = COracle(static, state, 9, dyn.tau, dyn.delta_t, scheme, np.float32)
     n = cells.face_indices.shape[0]
-    o.step(3)
-    t0 = time.perf_counter(); o.step(5); per = (time.perf_counter() - t0) / 5
+    o.step(2)
+    t0 = time.perf_counter(); o.step(3); per = (time.perf_counter() - t0) / 3
     iters = max(5, int(seconds / per))
     t0 = time.perf_counter(); o.step(iters); dt = time.perf_counter() - t0
     return {"value": n * iters / dt / 1e6, "unit": "MCUPS", "cores": threads(), "kind": "port",
-            "sample": f"{n} cells (nx=ny={nx}, same mesh family) x {iters} iterations, oracle/step_c.c OpenMP fp32; "
+            "sample": f"the same {n}-cell mesh x {iters} iterations, oracle/step_c.c OpenMP fp32; "
                       "JAX is not installed on the box so the reference's jitted CPU step cannot be timed"}
+
+
+def multi_gpu_check(rank, world, local_dev, scheme, real, nx=40, rows=24, iters=20):
+    """N>1 only, before the timed region: a small strip problem (nx x rows quads per rank) stepped through
+    the SAME native path as the benchmark (engine-owned NCCL send/recv inside fvdbm_step) must equal,
+    bit for bit, the whole mesh stepped by one handle on rank 0."""
+    import torch.distributed as dist
+    import fvdbm_jax_b200 as fb
+    from fvdbm_jax_b200.distributed import DistributedEnvironment, strip_local_mesh, containers_from_mesh
+    dyn = fb.D2Q9(tau=0.8, delta_t=0.1)
+    lm, fpc = strip_local_mesh(nx, rows, rank, world, dyn, scheme)
+    denv = DistributedEnvironment(lm, dyn, scheme, real, local_dev, 2 * nx * rows * world, fpc, native=True)
+    denv.step(iters)
+    denv.sync()
+    mine = (lm.cell_gid[:lm.n_owned].copy(), np.array(denv.env.cells.pdf[:lm.n_owned]), len(denv.engine.peers_recv))
+    denv.close()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    out = None
+    if rank == 0:
+        whole, _ = strip_local_mesh(nx, rows * world, 0, 1, dyn, scheme)
+        env = fb.Environment(*containers_from_mesh(whole.mesh, dyn, scheme), dtype=real, device=local_dev, reorder="hilbert")
+        env.init()
+        ref = np.empty((whole.n_owned, 9), dtype=real)
+        ref[whole.cell_gid[:whole.n_owned]] = env.step(iters).cells.pdf[:whole.n_owned]
+        env.close()
+        got = np.zeros_like(ref)
+        for gid, pdf, _ in parts:
+            got[gid] = pdf
+        out = {"bitwise_equal": bool(np.array_equal(got, ref)), "ranks": world, "cells": int(ref.shape[0]),
+               "iterations": iters, "peers_per_rank": [int(p[2]) for p in parts],
+               "what": f"{nx}x{rows}-quad strip per rank, native NCCL path vs one handle on rank 0"}
+    dist.barrier()
+    return out
 
 
 def run_reference(args):
@@ -131,12 +166,14 @@ def run_reference(args):
         return
     from oracle.step_c import COracle, threads, use_all_cores
     use_all_cores()
-    nx = args.ref_nx
+    nx = args.ref_nx if args.ref_nx > 0 else args.nx            # default: the GPU arm's own mesh
     m, dyn, cells, faces, nodes, _ = build_problem(nx, nx, args.scheme)
     static, state = static_state(cells, faces, nodes)
     o = COracle(static, state, 9, dyn.tau, dyn.delta_t, args.scheme, np.float32)
     n = cells.face_indices.shape[0]
-    inner = args.ref_inner
+    t0 = time.perf_counter(); o.step(1); t1 = time.perf_counter() - t0
+    # bounded sample: as many iterations per bench step as fit ~100 s for the whole --steps/--warmup run
+    inner = max(1, min(args.ref_inner, int(100.0 / ((args.steps + args.warmup) * t1))))
     for _ in range(args.warmup):
         o.step(inner)
     t0 = time.perf_counter()
@@ -144,11 +181,12 @@ def run_reference(args):
         o.step(inner)
     dt = time.perf_counter() - t0
     val = n * inner * args.steps / dt / 1e6
-    sample = f"{n} cells (nx=ny={nx}) x {inner} iterations per step, oracle/step_c.c OpenMP fp32"
+    sample = (f"{n} cells (nx=ny={nx}, {'the GPU arm mesh' if nx == args.nx else 'REDUCED mesh, same family'}) x {inner} "
+              f"iterations per bench step (the GPU arm runs {args.inner}), oracle/step_c.c OpenMP fp32 on {threads()} threads")
     line = {"impl": "reference", "metric": "MCUPS", "value": val, "unit": "MCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.nx, None, inner),
+            "config": workload_config(args, nx, n, args.inner),
             "cpu_baseline": {"value": val, "unit": "MCUPS", "cores": threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "MCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -159,7 +197,7 @@ def workload_config(args, nx, cells, inner):
     if getattr(args, "scaling", "weak") == "strong" and args.impl == "b200":
         shape = f"fixed global mesh nx={nx} x ny={args.ny_total} quads ({2 * nx * args.ny_total} cells) cut into one strip per GPU"
     else:
-        shape = f"nx=ny={nx} ({'%d cells' % cells if cells else '2*nx*ny cells'}) per GPU (weak scaling: strips of one global square)"
+        shape = f"nx=ny={nx} ({cells if cells else 2 * nx * nx} cells) per GPU (weak scaling: strips of one global square)"
     return {"workload": f"synthetic triangulated square, {shape}, x-periodic + y walls (lid 0.1), D2Q9 tau=0.8 dt=0.1, {args.scheme}",
             "inner_iterations_per_step": inner, "scheme": args.scheme, "l2": "inputs exceed L2 (no flush needed)",
             "reorder": args.reorder, "variant": args.variant, "tile_cells": args.tile, "stages": args.stages,
@@ -186,7 +224,8 @@ def main():
     ap.add_argument("--temporal", type=int, default=-1, help="1: temporal blocking (two iterations per pass), single GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ref-nx", type=int, default=1000)
+    ap.add_argument("--no-multi-gpu-check", action="store_true")
+    ap.add_argument("--ref-nx", type=int, default=0, help="reference arm mesh (0 = same as --nx)")
     ap.add_argument("--ref-inner", type=int, default=10)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: nx x nx quads per GPU (default); strong: a fixed nx x ny_total global mesh split into strips")
@@ -212,11 +251,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     real = np.float32 if args.dtype == "f32" else np.float64
+    problem, t_mesh, t_plan, mg_check = None, None, None, None
 
     if args.scaling == "strong" and args.ny_total % world:
         raise SystemExit("--ny-total must be divisible by the number of GPUs")
     if world > 1:
         from fvdbm_jax_b200.distributed import DistributedEnvironment
+        if not args.torch_exchange and not args.no_multi_gpu_check:
+            mg_check = multi_gpu_check(rank, world, local, args.scheme, real)
         rows = args.nx if args.scaling == "weak" else args.ny_total // world
         denv = DistributedEnvironment.strips(args.nx, rows, args.scheme, real, rank, world, local,
                                              native=not args.torch_exchange)
@@ -235,9 +277,12 @@ def main():
         stepper = env
     else:
         m, dyn, cells, faces, nodes, t_mesh = build_problem(args.nx, args.nx, args.scheme)
+        problem = (m, dyn, cells, faces, nodes)
         env = fb.Environment(cells, faces, nodes, dtype=real, device=local, reorder=args.reorder)
         env.init()
+        t0 = time.time()
         env.build()
+        t_plan = time.time() - t0
         n_local = n_global = cells.face_indices.shape[0]
         stepper = env
     for opt, val in ((_lib.OPT_VARIANT, args.variant), (_lib.OPT_TILE_CELLS, args.tile), (_lib.OPT_STAGES, args.stages)):
@@ -342,8 +387,12 @@ def main():
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, args.nx, n_local, inner), "roofline": roofline,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
+    if mg_check is not None:
+        line["multi_gpu_check"] = mg_check
+    if t_mesh is not None:
+        line["host_build_s"] = {"mesher": round(t_mesh, 2), "planner_and_upload": round(t_plan, 2)}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.scheme)
+        line["cpu_baseline"] = cpu_baseline(args.scheme, problem) if problem is not None else None
     os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         sys.stderr.flush()

@@ -139,25 +139,72 @@ def cylinder_channel(scale: int = 1, seed: int = 0) -> RawMesh:
                          seed=seed)
 
 
-def porous_channel(scale: int = 1, seed: int = 0, n_obst: int = 60) -> RawMesh:
-    """Porous-flow-like domain (tests/porous_flow.ipynb geometry: box (-93,0)-(279,186) with 60
-    obstacles); obstacles here are deterministic pseudo-random discs since the outline blob
-    (tests/test_bmp.mat) need not travel.  ``scale=4`` ~ 0.5M cells, ``scale=8`` ~ 2M cells (config 3)."""
+def points_in_polygon(px: np.ndarray, py: np.ndarray, poly: np.ndarray) -> np.ndarray:
+    """Even-odd (ray casting) test of many points against one closed polygon ``poly (V,2)``.
+    Only points inside the polygon's bounding box are tested; vectorised over points, looped over
+    the (few dozen) polygon edges."""
+    out = np.zeros(px.shape, dtype=bool)
+    x0, y0 = poly.min(axis=0)
+    x1, y1 = poly.max(axis=0)
+    cand = np.nonzero((px >= x0) & (px <= x1) & (py >= y0) & (py <= y1))[0]
+    if cand.size == 0:
+        return out
+    cx, cy = px[cand], py[cand]
+    inside = np.zeros(cand.size, dtype=bool)
+    ax, ay = poly[:, 0], poly[:, 1]
+    bx, by = np.roll(ax, -1), np.roll(ay, -1)
+    for i in range(poly.shape[0]):
+        if ay[i] == by[i]:
+            continue
+        crosses = (ay[i] > cy) != (by[i] > cy)
+        xi = ax[i] + (cy - ay[i]) * (bx[i] - ax[i]) / (by[i] - ay[i])
+        inside ^= crosses & (cx < xi)
+    out[cand] = inside
+    return out
+
+
+def porous_outlines():
+    """The 60 obstacle outlines of the reference's porous case (tests/test_bmp.mat as loaded by
+    tests/porous_flow.ipynb c7), one (V,2) float array per obstacle id, in the file's point order.
+    Data file written by oracle/make_porous_outlines.py."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "porous_outlines.npz"))
+    x, y, oid = d["x"].astype(np.float64), d["y"].astype(np.float64), d["id"]
+    return [np.stack([x[oid == i], y[oid == i]], axis=1) for i in np.unique(oid)]
+
+
+def porous_channel(scale: float = 1, seed: int = 0) -> RawMesh:
+    """Porous-flow domain of tests/porous_flow.ipynb (c7-c13): box (-93,0)-(279,186) minus the union
+    of the 60 obstacle polygons of tests/test_bmp.mat.  The notebook hands the outline to Triangle;
+    here (no Triangle) cells of a jittered structured triangulation whose centroid lies inside any
+    polygon are removed and the exposed nodes get the obstacle marker 5, as in c13
+    (``facet_markers=5``).  ``scale=1`` -> 186x93 quads, 27.5 k cells (porosity 0.795); ``scale=8.5`` -> 1.99 M cells =
+    BASELINE.json configs[2]."""
     lx, ly = 372.0, 186.0
-    nx, ny = 186 * scale, 93 * scale
-    rng = np.random.default_rng(1234 + seed)
-    cx = rng.uniform(0.12 * lx, 0.88 * lx, n_obst)
-    cy = rng.uniform(0.08 * ly, 0.92 * ly, n_obst)
-    r = rng.uniform(4.0, 9.0, n_obst)
+    nx, ny = int(round(186 * scale)), int(round(93 * scale))
+    polys = porous_outlines()
 
     def inside(x, y):
+        xs = x - 93.0                       # generator frame [0,372] -> notebook frame [-93,279]
         out = np.zeros(x.shape, dtype=bool)
-        for i in range(n_obst):
-            out |= (x - cx[i]) ** 2 + (y - cy[i]) ** 2 < r[i] ** 2
+        for poly in polys:
+            out |= points_in_polygon(xs, y, poly)
         return out
     m = masked_domain(nx, ny, lx, ly, inside, seed=seed)
     m.points[:, 0] -= 93.0
     return m
+
+
+def porous_boundary_conditions(mesher, nodes, rho_in: float = 1.05, rho_out: float = 0.95):
+    """Boundary conditions of tests/porous_flow.ipynb c26: obstacles (marker 5) and the two side walls
+    no-slip, density inlet / outlet on the remaining two box sides.  The notebook numbers the box
+    sides 1..4 in the order shapely returns the exterior ring (not reproducible here); the physical
+    reading is used: walls = bottom/top, inlet = left, outlet = right."""
+    for mk in (OBSTACLE, BOTTOM, TOP):
+        nodes = mesher.set_vel_node(nodes, mk, np.array([0.0, 0.0]))
+    nodes = mesher.set_rho_node(nodes, LEFT, rho_in)
+    nodes = mesher.set_rho_node(nodes, RIGHT, rho_out)
+    return nodes
 
 
 # ---------------------------------------------------------------------------------------------------

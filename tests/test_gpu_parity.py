@@ -291,11 +291,14 @@ def test_full_size_properties():
     rho_lag = env.cells.rho.copy()
     prev = np.empty((n, 9), np.float32)
     env.get_into("cells.pdf", prev)                     # current
-    env.set_option(_lib.OPT_VARIANT, _lib.VARIANT_DIRECT).set_option(_lib.OPT_REVERSE_SWEEP, 1)
-    env.cells.pdf = f0
-    env = env.step(4)
-    np.testing.assert_array_equal(env.cells.pdf, a)
-    np.testing.assert_array_equal(env.cells.rho, rho_lag)
+    assert env.info(_lib.INFO_VARIANT) == _lib.VARIANT_DIRECT          # the default kernel produced `a`
+    for variant, reverse in ((_lib.VARIANT_TMA, 0), (_lib.VARIANT_DIRECT, 1)):
+        env.set_option(_lib.OPT_VARIANT, variant).set_option(_lib.OPT_REVERSE_SWEEP, reverse)
+        assert env.info(_lib.INFO_VARIANT) == variant
+        env.cells.pdf = f0
+        env = env.step(4)
+        np.testing.assert_array_equal(env.cells.pdf, a)
+        np.testing.assert_array_equal(env.cells.rho, rho_lag)
     assert np.isfinite(a).all()
     assert abs(float(a.sum(dtype=np.float64)) / float(f0.sum(dtype=np.float64)) - 1) < 1e-4
     env.close()

