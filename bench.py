@@ -201,7 +201,7 @@ def workload_config(args, nx, cells, inner):
     return {"workload": f"synthetic triangulated square, {shape}, x-periodic + y walls (lid 0.1), D2Q9 tau=0.8 dt=0.1, {args.scheme}",
             "inner_iterations_per_step": inner, "scheme": args.scheme, "l2": "inputs exceed L2 (no flush needed)",
             "reorder": args.reorder, "variant": args.variant, "tile_cells": args.tile, "stages": args.stages,
-            "reverse_sweep": args.reverse, "graph_steps": args.graph, "temporal": getattr(args, "temporal", -1)}
+            "reverse_sweep": args.reverse, "graph_steps": args.graph}
 
 
 def main():
@@ -221,7 +221,6 @@ def main():
     ap.add_argument("--reverse", type=int, default=-1)
     ap.add_argument("--graph", type=int, default=-1)
     ap.add_argument("--ctas", type=int, default=-1)
-    ap.add_argument("--temporal", type=int, default=-1, help="1: temporal blocking (two iterations per pass), single GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-multi-gpu-check", action="store_true")
@@ -288,8 +287,7 @@ def main():
     for opt, val in ((_lib.OPT_VARIANT, args.variant), (_lib.OPT_TILE_CELLS, args.tile), (_lib.OPT_STAGES, args.stages)):
         if val > 0:
             stepper.set_option(opt, val)
-    for opt, val in ((_lib.OPT_REVERSE_SWEEP, args.reverse), (_lib.OPT_GRAPH_STEPS, args.graph), (_lib.OPT_CTAS_PER_SM, args.ctas),
-                     (_lib.OPT_TEMPORAL, args.temporal if world == 1 else -1)):
+    for opt, val in ((_lib.OPT_REVERSE_SWEEP, args.reverse), (_lib.OPT_GRAPH_STEPS, args.graph), (_lib.OPT_CTAS_PER_SM, args.ctas)):
         if val >= 0:
             stepper.set_option(opt, val)
 
@@ -371,7 +369,7 @@ def main():
     iter_ms = ms / (inner * args.steps)
     achieved = n_local * b_alg / (iter_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_fused_tma" if n_launch_info == 2 else "k_fused_direct",
+                "traffic": None, "kernel": {1: "k_fused_direct", 2: "k_fused_tma", 3: "k_fused_pair"}.get(n_launch_info, "?"),
                 "algorithmic_bytes_per_cell_update": b_alg, "cells_per_launch": n_local, "avg_launch_ms": iter_ms,
                 "peak_source": peak_src,
                 "note": "avg_launch_ms = event time / iterations (includes the O(sqrt N) node kernel); traffic from "

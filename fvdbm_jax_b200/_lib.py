@@ -14,12 +14,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FVDBM_LIB", os.path.join(HERE, "libfvdbm_b200.so"))   # FVDBM_LIB: A/B builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 COMM_ID_BYTES = 128
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 SCHEME_UPWIND, SCHEME_LAX_WENDROFF = 0, 1
 MODE_AUTO, MODE_STAGED, MODE_FUSED = 0, 1, 2
-VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA = 0, 1, 2
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA, VARIANT_PAIR = 0, 1, 2, 3
 (CELL_PDF, CELL_RHO, CELL_VEL, CELL_PDF_EQ, FACE_FLUX, NODE_PDF, NODE_RHO, NODE_VEL,
  CELL_PDF_PREV) = range(9)
 (INFO_MODE, INFO_STEPS, INFO_LAUNCHES, INFO_TRACKED_NODES, INFO_BOUNDARY_SIDES, INFO_DEVICE_BYTES,
@@ -48,6 +48,7 @@ class Desc(C.Structure):
         ("face_L", C.c_void_p), ("node_type", C.c_void_p), ("node_cell_idx", C.c_void_p),
         ("node_cell_dist", C.c_void_p), ("cell_pdf", C.c_void_p), ("node_pdf", C.c_void_p),
         ("node_rho", C.c_void_p), ("node_vel", C.c_void_p), ("cell_perm", C.c_void_p),
+        ("cell_inv_area", C.c_void_p),
     ]
 
 
@@ -132,7 +133,7 @@ class DescArrays:
     def __init__(self, *, dtype, scheme, Q, K, tau, delta_t, lattice_constants,
                  cell_face_idx, cell_face_sign, face_cell_idx, face_dists, face_node_idx, face_n, face_L,
                  node_type, node_cell_idx, node_cell_dist, cell_pdf, node_pdf, node_rho, node_vel,
-                 cell_perm=None, n_owned=0, device_id=0, mode=MODE_AUTO):
+                 cell_perm=None, n_owned=0, device_id=0, mode=MODE_AUTO, cell_inv_area=None):
         real = np.dtype(dtype)
         if real not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise ValueError("dtype must be float32 or float64")
@@ -175,6 +176,8 @@ class DescArrays:
         arr("node_vel", node_vel, real, (Pn, 2))
         if cell_perm is not None:
             arr("cell_perm", cell_perm, np.int32, (N,))
+        if cell_inv_area is not None:
+            arr("cell_inv_area", cell_inv_area, real, (N,))
         self.N, self.F, self.P, self.M, self.Q, self.K = N, F, Pn, M, Q, K
 
         d = self.desc = Desc()
@@ -194,6 +197,7 @@ class DescArrays:
                      "node_vel"):
             setattr(d, name, keep[name].ctypes.data)
         d.cell_perm = keep["cell_perm"].ctypes.data if cell_perm is not None else None
+        d.cell_inv_area = keep["cell_inv_area"].ctypes.data if cell_inv_area is not None else None
 
 
 class HostPlan:
@@ -234,5 +238,5 @@ class HostPlan:
             pass
 
 
-_PLAN_I32 = {"ring_fcell", "t2_off", "t2_n1", "t2_pos", "l2_list", "pos", "ipos", "ccode", "cface", "bt_off", "bt_nodes", "bf_la", "bf_lb", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
+_PLAN_I32 = {"ring_fcell", "pos", "ipos", "ccode", "bf_na", "bf_nb", "tn_orig", "tn_type", "node_track", "ring_off",
              "ring_cell", "s_cface", "s_csign", "s_fcell", "s_fnode"}

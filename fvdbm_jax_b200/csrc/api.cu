@@ -127,35 +127,24 @@ struct EngineT final : Engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap = 1;
     int mode = FVDBM_MODE_FUSED;
-    int variant = FVDBM_VARIANT_DIRECT;   // measured: 97% of the HBM roofline at 10M cells vs 82-90% for TMA
+    int variant = FVDBM_VARIANT_DIRECT;   // fp32: PAIR (two cells per thread, packed math); fp64: DIRECT; TMA is opt-in
     int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
     int num_sms = 148;
     int cur = 0;
     int64_t steps = 0, launches = 0;
     bool phase0_done = false;
 
-    DevBuf<real> pdf[3];                 // ping-pong (2) or, with temporal blocking, a 3-buffer rotation
-    int nbuf = 2, prev = 1;              // prev = buffer holding the populations before the last iteration
-    int temporal = 0;                    // 1: two iterations per pass over overlapped tiles (k_fused2)
-    DevBuf<int32_t> t2_off, t2_n1, t2_pos, l2_list;
-    DevBuf<int64_t> t2_loff;
-    DevBuf<uint16_t> t2_lnbr;
-    size_t t2_smem = 0;
-    int nxt() const { return (cur + 1) % nbuf; }
+    DevBuf<real> pdf[2];                 // ping-pong: pdf[prev] *is* the lagged state of the reference's observables
+    int prev = 1;                        // buffer holding the populations before the last iteration
+    int nxt() const { return cur ^ 1; }
     DevBuf<int32_t> ccode, bf_na, bf_nb, pos, ipos, ring_off, ring_cell, tn_type;
-    DevBuf<real> ccoef, fcoef, bf_ratio, ring_w, npdf, nrho, nvel;
-    DevBuf<int32_t> cface;
-    int layout = 0;                      // 0: per-side coefficients (default, coalesced); 1: shared face records
-                                         // (12 B/cell fewer, but measured 7% slower: 16 B gathers)
+    DevBuf<real> ccoef, bf_ratio, ring_w, npdf, nrho, nvel, s_inv_area;
     DevBuf<int32_t> s_cface, s_csign, s_fcell, s_fnode;
     DevBuf<real> s_fdist, s_fn, s_fL;
     DevBuf<real> s_rho, s_ux, s_uy, s_feq, s_flux;     // staged dynamics (lazy)
     DevBuf<real> scratch;                              // export/import staging
-    DevBuf<int32_t> halo_send, halo_recv, bt_off, bt_nodes, bf_la, bf_lb;
+    DevBuf<int32_t> halo_send, halo_recv;
     DevBuf<unsigned long long> counter;
-    int border_fused = 0;                // 0 (default): k_nodes, then the cell kernel over the border tiles;
-                                         // 1: k_border, both in one launch -- measured 9x SLOWER on small meshes
-                                         // (per-tile node evaluation serialises the latency chains)
     // native exchange (optional)
     ncclComm_t comm = nullptr;
     std::vector<int> send_peers, recv_peers;
@@ -213,6 +202,7 @@ struct EngineT final : Engine {
             if (d.mode == FVDBM_MODE_FUSED) { err = "fused mode unavailable: " + plan.why_not; return FVDBM_ERR_ARG; }
             mode = FVDBM_MODE_STAGED;
         }
+        if (mode == FVDBM_MODE_STAGED && plan.No < plan.N) { err = "staged mode does not support halo cells"; return FVDBM_ERR_ARG; }
         const size_t npdf_elems = (size_t)(plan.Npad / TW) * Q * TW;
         CU_TRY(pdf[0].alloc(npdf_elems));
         CU_TRY(pdf[1].alloc(npdf_elems));
@@ -221,32 +211,13 @@ struct EngineT final : Engine {
         CU_TRY(pos.upload(plan.pos, stream));
         CU_TRY(ipos.upload(plan.ipos, stream));
         if (plan.fused_ok) {
-            if (const char* e = getenv("FVDBM_COEF_LAYOUT")) layout = atoi(e) ? 1 : 0;
             CU_TRY(ccode.upload(plan.ccode, stream));
-            if (layout == 0) CU_TRY(ccoef.upload(plan.ccoef, stream));
-            else { CU_TRY(cface.upload(plan.cface, stream)); CU_TRY(fcoef.upload(plan.fcoef, stream)); }
+            CU_TRY(ccoef.upload(plan.ccoef, stream));
             CU_TRY(bf_na.upload(plan.bf_na, stream));
             CU_TRY(bf_nb.upload(plan.bf_nb, stream));
             CU_TRY(bf_ratio.upload(plan.bf_ratio, stream));
-            if (plan.t2_ok) {
-                CU_TRY(t2_off.upload(plan.t2_off, stream)); CU_TRY(t2_n1.upload(plan.t2_n1, stream));
-                CU_TRY(t2_pos.upload(plan.t2_pos, stream)); CU_TRY(t2_loff.upload(plan.t2_loff, stream));
-                CU_TRY(t2_lnbr.upload(plan.t2_lnbr, stream)); CU_TRY(l2_list.upload(plan.l2_list, stream));
-                s0_stride = (int)round_up(plan.t2_max_entries, 32); s1_stride = (int)round_up(plan.t2_max_n01, 32);
-                t2_smem = (size_t)Q * (s0_stride + s1_stride) * sizeof(real);
-                CU_TRY(cudaFuncSetAttribute(k_fused2<real, Q, K, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)prop.sharedMemPerBlockOptin));
-            }
-            CU_TRY(bt_off.upload(plan.bt_off, stream));
-            CU_TRY(bt_nodes.upload(plan.bt_nodes, stream));
-            CU_TRY(bf_la.upload(plan.bf_la, stream));
-            CU_TRY(bf_lb.upload(plan.bf_lb, stream));
-            if (const char* e = getenv("FVDBM_BORDER_FUSED")) border_fused = atoi(e) ? 1 : 0;
-            border_smem = (size_t)std::max<int64_t>(plan.max_tile_nodes, 1) * Q * sizeof(real);
-            if (border_smem > prop.sharedMemPerBlockOptin) border_fused = 0;
-            CU_TRY(cudaFuncSetAttribute(k_border<real, Q, K, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)prop.sharedMemPerBlockOptin));
         }
+        CU_TRY(s_inv_area.upload(plan.s_inv_area, stream));
         CU_TRY(ring_cell.upload(plan.ring_fcell, stream));     // fixed-width ring table [NA][MR]
         CU_TRY(ring_w.upload(plan.ring_fw, stream));
         CU_TRY(tn_type.upload(plan.tn_type, stream));
@@ -262,16 +233,18 @@ struct EngineT final : Engine {
         CU_TRY(s_fL.upload(static_cast<const real*>(d.face_L), (size_t)plan.F, stream));
         CU_TRY(cudaStreamSynchronize(stream));
         // host staging vectors are no longer needed
-        plan.ccode = {}; plan.ccoef = {}; plan.cface = {}; plan.fcoef = {}; plan.s_cface = {}; plan.s_csign = {}; plan.s_fcell = {}; plan.s_fnode = {};
-        plan.ring_cell = {}; plan.ring_w = {}; plan.ring_fcell = {}; plan.ring_fw = {}; plan.tn_pdf = {}; plan.t2_pos = {}; plan.t2_lnbr = {}; plan.bt_nodes = {}; plan.bf_la = {}; plan.bf_lb = {};
+        plan.ccode = {}; plan.ccoef = {}; plan.s_cface = {}; plan.s_csign = {}; plan.s_fcell = {}; plan.s_fnode = {};
+        plan.ring_cell = {}; plan.ring_w = {}; plan.ring_fcell = {}; plan.ring_fw = {}; plan.tn_pdf = {}; plan.s_inv_area = {};
         int rc = set(FVDBM_CELL_PDF, d.cell_pdf, (size_t)plan.N * Q * sizeof(real));
         if (rc) return rc;
         // opt-in shared memory for the TMA kernel
-        CU_TRY(cudaFuncSetAttribute(k_fused_tma<real, Q, K, SCHEME, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)prop.sharedMemPerBlockOptin));
-        CU_TRY(cudaFuncSetAttribute(k_fused_tma<real, Q, K, SCHEME, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU_TRY(cudaFuncSetAttribute(k_fused_tma<real, Q, K, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)prop.sharedMemPerBlockOptin));
         max_smem = prop.sharedMemPerBlockOptin;
+        variant = default_variant();
+        // debugging / A-B overrides of the defaults (documented in include/fvdbm_b200.h; the same knobs are
+        // reachable through fvdbm_set_option): FVDBM_VARIANT, FVDBM_TILE_CELLS, FVDBM_STAGES,
+        // FVDBM_GRAPH_STEPS, FVDBM_CTAS_PER_SM, FVDBM_REVERSE_SWEEP, FVDBM_OVERLAP
         if (const char* e = getenv("FVDBM_VARIANT")) variant = atoi(e);
         if (const char* e = getenv("FVDBM_TILE_CELLS")) tile_cells = atoi(e);
         if (const char* e = getenv("FVDBM_STAGES")) stages = atoi(e);
@@ -280,20 +253,18 @@ struct EngineT final : Engine {
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
-        if (const char* e = getenv("FVDBM_TEMPORAL")) { int rc2 = set_temporal(atoi(e)); if (rc2) return rc2; }
-        if (variant == FVDBM_VARIANT_AUTO) variant = FVDBM_VARIANT_DIRECT;
+        if (variant == FVDBM_VARIANT_AUTO) variant = default_variant();
         return sanitize_options();
     }
-    size_t max_smem = 0, border_smem = 0;
-    int s0_stride = 0, s1_stride = 0;
+    size_t max_smem = 0;
     int occ_cache = 0;
+    static constexpr int default_variant() { return sizeof(real) == 4 ? FVDBM_VARIANT_PAIR : FVDBM_VARIANT_DIRECT; }
 
-    size_t stage_bytes(int tc) const {
-        return layout == 0 ? tma_stage_bytes<real, Q, K, SCHEME, 0>(tc) : tma_stage_bytes<real, Q, K, SCHEME, 1>(tc);
-    }
+    size_t stage_bytes(int tc) const { return tma_stage_bytes<real, Q, K, SCHEME>(tc); }
 
     int sanitize_options() {
-        if (variant != FVDBM_VARIANT_DIRECT && variant != FVDBM_VARIANT_TMA) { err = "unknown variant"; return FVDBM_ERR_ARG; }
+        if (variant != FVDBM_VARIANT_DIRECT && variant != FVDBM_VARIANT_TMA && variant != FVDBM_VARIANT_PAIR) { err = "unknown variant"; return FVDBM_ERR_ARG; }
+        if (variant == FVDBM_VARIANT_PAIR && sizeof(real) != 4) { err = "the packed two-cells-per-thread kernel exists for fp32 only"; return FVDBM_ERR_ARG; }
         if (tile_cells != 128 && tile_cells != 256 && tile_cells != 512) { err = "tile_cells must be 128, 256 or 512"; return FVDBM_ERR_ARG; }
         if (stages < 2 || stages > 8) { err = "stages must be in 2..8"; return FVDBM_ERR_ARG; }
         while (stages > 2 && kTmaHeader + stages * stage_bytes(tile_cells) > max_smem) --stages;
@@ -308,8 +279,7 @@ struct EngineT final : Engine {
         FusedArgs<real> a;
         a.P = P;
         a.pdf_in = pdf[cur].p; a.pdf_out = pdf[nxt()].p;
-        a.list = nullptr; a.list_n = 0;
-        a.ccode = ccode.p; a.ccoef = ccoef.p; a.cface = cface.p; a.fcoef = fcoef.p;
+        a.ccode = ccode.p; a.ccoef = ccoef.p;
         a.G.bf_na = bf_na.p; a.G.bf_nb = bf_nb.p; a.G.bf_ratio = bf_ratio.p;
         a.G.npdf = npdf.p; a.G.NTpad = plan.NTpad;
         a.cell_begin = begin; a.cell_end = end;
@@ -324,12 +294,8 @@ struct EngineT final : Engine {
         a.npdf = npdf.p; a.nrho = nrho.p; a.nvel = nvel.p; a.NTpad = plan.NTpad; a.NA = (int)count;
         return a;
     }
-    bool use_border_kernel() const { return mode == FVDBM_MODE_FUSED && border_fused; }
-
-    // node kernel: every active node (staged mode / unfused border), or only the "orphans" that no
-    // boundary side references when the border kernel evaluates the rest tile by tile
     int launch_nodes() {
-        const int64_t count = use_border_kernel() ? plan.NO : plan.NA;
+        const int64_t count = plan.NA;
         if (count == 0) return FVDBM_OK;
         NodeArgs<real> a = node_args(count);
         k_nodes<real, Q><<<blocks_for(count * 32, 256), 256, 0, stream>>>(a);
@@ -341,16 +307,16 @@ struct EngineT final : Engine {
     int launch_fused(int64_t begin, int64_t end, cudaStream_t st) {
         if (end <= begin) return FVDBM_OK;
         FusedArgs<real> a = fused_args(begin, end);
-        if (variant == FVDBM_VARIANT_DIRECT) {
-            if (layout == 0) k_fused_direct<real, Q, K, SCHEME, 0><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
-            else k_fused_direct<real, Q, K, SCHEME, 1><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
+        if (variant == FVDBM_VARIANT_PAIR) {
+            launch_pair(a, end - begin, st);
+        } else if (variant == FVDBM_VARIANT_DIRECT) {
+            k_fused_direct<real, Q, K, SCHEME><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
         } else {
             const size_t smem = kTmaHeader + (size_t)stages * stage_bytes(tile_cells);
             int per_sm = ctas_per_sm;
             if (per_sm <= 0) {
                 if (occ_cache <= 0) {
-                    if (layout == 0) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_fused_tma<real, Q, K, SCHEME, 0>, tile_cells, smem));
-                    else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_fused_tma<real, Q, K, SCHEME, 1>, tile_cells, smem));
+                    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_fused_tma<real, Q, K, SCHEME>, tile_cells, smem));
                     if (occ_cache < 1) occ_cache = 1;
                 }
                 per_sm = occ_cache;
@@ -358,28 +324,18 @@ struct EngineT final : Engine {
             const int64_t ntiles = (end - begin) / tile_cells;
             int64_t grid = (int64_t)num_sms * per_sm;
             if (grid > ntiles) grid = ntiles;
-            if (layout == 0) k_fused_tma<real, Q, K, SCHEME, 0><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
-            else k_fused_tma<real, Q, K, SCHEME, 1><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
+            k_fused_tma<real, Q, K, SCHEME><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
         }
         ++launches;
         CU_TRY(cudaGetLastError());
         return FVDBM_OK;
     }
 
-    int launch_border() {
-        const int64_t begin = plan.Bstart, end = owned_end();
-        if (end <= begin) return FVDBM_OK;
-        BorderArgs<real> b;
-        b.F = fused_args(begin, end);
-        b.F.reverse = 0;
-        if (layout == 0) b.F.cface = nullptr;          // k_border picks the coefficient layout from this
-        b.N = node_args(plan.NA);
-        b.bt_off = bt_off.p; b.bt_nodes = bt_nodes.p; b.bf_la = bf_la.p; b.bf_lb = bf_lb.p;
-        k_border<real, Q, K, SCHEME><<<(unsigned)((end - begin) / BORDER_TILE), BORDER_TILE, border_smem, stream>>>(b);
-        ++launches;
-        CU_TRY(cudaGetLastError());
-        return FVDBM_OK;
+    // fp32 only: two cells per thread, 128 threads (= 256 cells) per CTA
+    void launch_pair(const FusedArgs<float>& a, int64_t cells, cudaStream_t st) {
+        k_fused_pair<Q, K, SCHEME><<<blocks_for(cells / 2, 128), 128, 0, st>>>(a);
     }
+    void launch_pair(const FusedArgs<double>&, int64_t, cudaStream_t) {}
 
     int ensure_staged_buffers() {
         if (s_flux.p) return FVDBM_OK;
@@ -411,12 +367,9 @@ struct EngineT final : Engine {
         if ((rc = launch_nodes())) return rc;
         if ((rc = launch_faces(pdf[cur].p))) return rc;
         k_s_cells<real, Q, K><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, pdf[cur].p, s_feq.p, s_flux.p, s_cface.p,
-                                                                            s_csign.p, ipos.p, plan.Npad, plan.No, pdf[nxt()].p);
+                                                                            s_csign.p, ipos.p, plan.Npad, plan.No, s_inv_area.p, pdf[nxt()].p);
         ++launches;
         CU_TRY(cudaGetLastError());
-        if (plan.No < plan.N) {   // halo copies are refreshed by the caller; keep them readable in both buffers
-            err = "staged mode does not support halo cells"; return FVDBM_ERR_STATE;
-        }
         prev = cur; cur = nxt(); ++steps;
         return FVDBM_OK;
     }
@@ -447,8 +400,7 @@ struct EngineT final : Engine {
         if (!phase0_done && (rc = fork_interior())) return rc;       // fork first: the exchange must not delay it
         if (xchg && (rc = exchange())) return rc;
         if ((rc = launch_nodes())) return rc;
-        if (use_border_kernel()) { if ((rc = launch_border())) return rc; }
-        else if ((rc = launch_fused(plan.Bstart, owned_end(), stream))) return rc;
+        if ((rc = launch_fused(plan.Bstart, owned_end(), stream))) return rc;
         if (forked) CU_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
         forked = false;
         phase0_done = false;
@@ -483,7 +435,6 @@ struct EngineT final : Engine {
             off += (size_t)recv_counts[i];
         }
         NCCL_TRY(g_nccl.GroupEnd());
-        launches += 1;
         return halo_unpack(recvbuf.p);
     }
 
@@ -512,71 +463,6 @@ struct EngineT final : Engine {
         CU_TRY(sendbuf.alloc((size_t)std::max<int64_t>(tot_s, 1) * Q));
         CU_TRY(recvbuf.alloc((size_t)std::max<int64_t>(tot_r, 1) * Q));
         drop_graphs();
-        return FVDBM_OK;
-    }
-
-    // ---- temporal blocking --------------------------------------------------------------------------
-    bool temporal_possible() const {
-        return mode == FVDBM_MODE_FUSED && plan.t2_ok && plan.No == plan.N && variant == FVDBM_VARIANT_DIRECT &&
-               layout == 0 && t2_smem > 0 && t2_smem <= max_smem;
-    }
-    int set_temporal(int on) {
-        if (!on) { temporal = 0; return FVDBM_OK; }
-        if (!temporal_possible()) { err = "temporal blocking needs the fused direct kernel on a single-GPU handle"; return FVDBM_ERR_STATE; }
-        if (nbuf == 2) {                       // third buffer, copy of nothing in particular: holes must be zero
-            CU_TRY(pdf[2].alloc(pdf[0].n));
-            CU_TRY(cudaMemsetAsync(pdf[2].p, 0, pdf[2].bytes(), stream));
-            nbuf = 3;
-        }
-        temporal = 1; graph_steps = 0; drop_graphs();
-        return FVDBM_OK;
-    }
-
-    // Two iterations A(t) -> C(t+2).  Side stream: k_fused2 over the tiles (cells at level >= 2).
-    // Main stream: nodes(A); level<=2 cells A->B (list + range); nodes(B); level<=1 cells B->C.
-    int superstep() {
-        const int A = cur, B = (cur + 1) % 3, C = (cur + 2) % 3;
-        const int64_t end = owned_end();
-        CU_TRY(cudaEventRecord(ev_fork, stream));
-        CU_TRY(cudaStreamWaitEvent(stream2, ev_fork, 0));
-        {
-            Fused2Args<real> t;
-            t.P = P; t.pdf_in = pdf[A].p; t.pdf_out = pdf[C].p; t.ccoef = ccoef.p;
-            t.t2_off = t2_off.p; t.t2_n1 = t2_n1.p; t.t2_pos = t2_pos.p; t.t2_loff = t2_loff.p; t.t2_lnbr = t2_lnbr.p;
-            t.s0_stride = s0_stride; t.s1_stride = s1_stride;
-            k_fused2<real, Q, K, SCHEME><<<(unsigned)plan.t2_tiles, 256, t2_smem, stream2>>>(t);
-            ++launches;
-            CU_TRY(cudaGetLastError());
-        }
-        CU_TRY(cudaEventRecord(ev_join, stream2));
-        int rc;
-        auto thin = [&](int in, int out, bool with_list) -> int {
-            cur = in;                                            // node kernel + fused_args read pdf[cur]
-            int r = launch_nodes();
-            if (r) return r;
-            if (with_list && l2_list.n) {
-                FusedArgs<real> a = fused_args(0, 0);
-                a.pdf_out = pdf[out].p; a.list = l2_list.p; a.list_n = (int64_t)l2_list.n; a.reverse = 0;
-                k_fused_direct<real, Q, K, SCHEME, 0><<<blocks_for((int64_t)l2_list.n, 256), 256, 0, stream>>>(a);
-                ++launches;
-                CU_TRY(cudaGetLastError());
-            }
-            if (end > plan.D1start) {
-                FusedArgs<real> a = fused_args(plan.D1start, end);
-                a.pdf_out = pdf[out].p; a.reverse = 0;
-                k_fused_direct<real, Q, K, SCHEME, 0><<<blocks_for(end - plan.D1start, 256), 256, 0, stream>>>(a);
-                ++launches;
-                CU_TRY(cudaGetLastError());
-            }
-            return FVDBM_OK;
-        };
-        rc = thin(A, B, true);
-        if (!rc) rc = thin(B, C, false);
-        cur = A;
-        if (rc) return rc;
-        CU_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
-        prev = B;                  // only valid near the boundary: step() always finishes with a single step
-        cur = C; steps += 2;
         return FVDBM_OK;
     }
 
@@ -615,14 +501,8 @@ struct EngineT final : Engine {
         CU_TRY(cudaSetDevice(device));
         int rc;
         if (mode == FVDBM_MODE_STAGED && (rc = ensure_staged_buffers())) return rc;
-        // temporal blocking: pairs of iterations, but the last iteration is always a single step so that
-        // the lagged observables (rho/vel/pdf_eq/flux of the previous populations) stay exact
-        while (temporal && n >= 3 && !phase0_done && !native_exchange()) {
-            if ((rc = superstep())) return rc;
-            n -= 2;
-        }
         while (n > 0) {
-            if (graph_steps > 0 && nbuf == 2 && n >= graph_steps && !phase0_done && !native_exchange()) {   // NCCL ops stay out of graphs
+            if (graph_steps > 0 && n >= graph_steps && !phase0_done && !native_exchange()) {   // NCCL ops stay out of graphs
                 auto it = graphs.find(cur);
                 if (it == graphs.end()) {
                     cudaGraphExec_t ge;
@@ -646,9 +526,9 @@ struct EngineT final : Engine {
 
     int64_t launches_per_step() const {
         if (mode == FVDBM_MODE_STAGED) return 3 + (plan.NA > 0 ? 1 : 0);
-        const int64_t nodes = use_border_kernel() ? plan.NO : plan.NA;
-        return (nodes > 0 ? 1 : 0) + (plan.Bstart > 0 ? 1 : 0) + (owned_end() > plan.Bstart ? 1 : 0) +
-               (native_exchange() ? 3 : 0);
+        // own kernels only: the grouped ncclSend/Recv of a native exchange is NCCL's launch, not counted
+        return (plan.NA > 0 ? 1 : 0) + (plan.Bstart > 0 ? 1 : 0) + (owned_end() > plan.Bstart ? 1 : 0) +
+               (native_exchange() ? (halo_send.n ? 1 : 0) + (halo_recv.n ? 1 : 0) : 0);
     }
 
     int step_timed(int n, float* ms) override {
@@ -809,13 +689,15 @@ struct EngineT final : Engine {
     int set_option(int opt, int64_t v) override {
         const int old_variant = variant, old_tile = tile_cells, old_stages = stages, old_graph = graph_steps;
         switch (opt) {
-        case FVDBM_OPT_VARIANT: variant = v == FVDBM_VARIANT_AUTO ? FVDBM_VARIANT_DIRECT : (int)v; break;
+        case FVDBM_OPT_VARIANT: variant = v == FVDBM_VARIANT_AUTO ? default_variant() : (int)v; break;
         case FVDBM_OPT_TILE_CELLS: tile_cells = (int)v; break;
         case FVDBM_OPT_STAGES: stages = (int)v; break;
         case FVDBM_OPT_GRAPH_STEPS: graph_steps = (int)v; break;
         case FVDBM_OPT_CTAS_PER_SM: ctas_per_sm = (int)v; break;
         case FVDBM_OPT_REVERSE_SWEEP: reverse_sweep = v ? 1 : 0; break;
-        case FVDBM_OPT_TEMPORAL: { int rc2 = set_temporal((int)v); if (rc2) return rc2; break; }
+        case FVDBM_OPT_TEMPORAL:
+            if (v) { err = "temporal blocking was removed in ABI 2 (measured slower than the single-step kernel; DESIGN.md)"; return FVDBM_ERR_UNSUPPORTED; }
+            break;
         default: err = "unknown option"; return FVDBM_ERR_ARG;
         }
         occ_cache = 0;
@@ -834,9 +716,12 @@ struct EngineT final : Engine {
         case FVDBM_INFO_TRACKED_NODES: *v = plan.NT; break;
         case FVDBM_INFO_BOUNDARY_SIDES: *v = plan.NB; break;
         case FVDBM_INFO_DEVICE_BYTES:
-            *v = (int64_t)(pdf[0].bytes() * 2 + ccode.bytes() + ccoef.bytes() + cface.bytes() + fcoef.bytes() + s_cface.bytes() * 2 + s_fcell.bytes() * 2 +
-                           s_fdist.bytes() * 2 + s_fL.bytes() + pos.bytes() + ipos.bytes() + s_flux.bytes() + s_feq.bytes() +
-                           scratch.bytes());
+            *v = (int64_t)(pdf[0].bytes() + pdf[1].bytes() + ccode.bytes() + ccoef.bytes() + bf_na.bytes() + bf_nb.bytes() +
+                           bf_ratio.bytes() + pos.bytes() + ipos.bytes() + ring_cell.bytes() + ring_w.bytes() + tn_type.bytes() +
+                           npdf.bytes() + nrho.bytes() + nvel.bytes() + s_cface.bytes() + s_csign.bytes() + s_fcell.bytes() +
+                           s_fnode.bytes() + s_fdist.bytes() + s_fn.bytes() + s_fL.bytes() + s_inv_area.bytes() + s_rho.bytes() +
+                           s_ux.bytes() + s_uy.bytes() + s_feq.bytes() + s_flux.bytes() + scratch.bytes() + halo_send.bytes() +
+                           halo_recv.bytes() + sendbuf.bytes() + recvbuf.bytes() + counter.bytes());
             break;
         case FVDBM_INFO_VARIANT: *v = variant; break;
         case FVDBM_INFO_NPAD: *v = plan.Npad; break;
@@ -921,9 +806,9 @@ template <typename real>
 int64_t plan_array(const Plan<real>& p, const std::string& k, const void** ptr, int32_t* eb) {
 #define I32(name) if (k == #name) { *ptr = p.name.data(); *eb = 4; return (int64_t)p.name.size(); }
 #define REAL(name) if (k == #name) { *ptr = p.name.data(); *eb = (int32_t)sizeof(real); return (int64_t)p.name.size(); }
-    I32(pos) I32(ipos) I32(ccode) I32(cface) I32(bf_na) I32(bf_nb) I32(tn_orig) I32(tn_type) I32(node_track)
-    I32(t2_off) I32(t2_n1) I32(t2_pos) I32(l2_list) I32(bt_off) I32(bt_nodes) I32(bf_la) I32(bf_lb) I32(ring_off) I32(ring_cell) I32(s_cface) I32(s_csign) I32(s_fcell) I32(s_fnode)
-    REAL(ccoef) REAL(fcoef) REAL(bf_ratio) REAL(ring_w) REAL(ring_fw) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel)
+    I32(pos) I32(ipos) I32(ccode) I32(bf_na) I32(bf_nb) I32(tn_orig) I32(tn_type) I32(node_track)
+    I32(ring_off) I32(ring_cell) I32(ring_fcell) I32(s_cface) I32(s_csign) I32(s_fcell) I32(s_fnode)
+    REAL(ccoef) REAL(bf_ratio) REAL(ring_w) REAL(ring_fw) REAL(tn_pdf) REAL(tn_rho) REAL(tn_vel) REAL(s_inv_area)
 #undef I32
 #undef REAL
     return -1;
@@ -932,11 +817,8 @@ template <typename real>
 int64_t plan_scalar(const Plan<real>& p, const std::string& k) {
     if (k == "N") return p.N; if (k == "F") return p.F; if (k == "P") return p.P; if (k == "No") return p.No;
     if (k == "Npad") return p.Npad; if (k == "Bstart") return p.Bstart; if (k == "Oend") return p.Oend;
-    if (k == "Hstart") return p.Hstart; if (k == "D1start") return p.D1start;
-    if (k == "t2_tiles") return p.t2_tiles; if (k == "t2_max_entries") return p.t2_max_entries;
-    if (k == "t2_max_n01") return p.t2_max_n01; if (k == "t2_ok") return p.t2_ok ? 1 : 0; if (k == "NB") return p.NB; if (k == "NT") return p.NT;
-    if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "NF") return p.NF; if (k == "NO") return p.NO; if (k == "MR") return p.MR;
-    if (k == "max_tile_nodes") return p.max_tile_nodes; if (k == "NC") return p.NC;
+    if (k == "Hstart") return p.Hstart; if (k == "NB") return p.NB; if (k == "NT") return p.NT;
+    if (k == "NTpad") return p.NTpad; if (k == "NA") return p.NA; if (k == "MR") return p.MR; if (k == "NC") return p.NC;
     if (k == "fused_ok") return p.fused_ok ? 1 : 0;
     return -1;
 }

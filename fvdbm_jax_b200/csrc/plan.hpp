@@ -1,6 +1,7 @@
 // plan.hpp -- host-side planning: reference layout (AoS, original numbering) -> device layout.
 //
-// Pure C++ (no CUDA) so it can be exercised on a CPU-only box through fvdbm_plan_create().
+// Pure C++ (no CUDA) so it can be exercised on a CPU-only box through fvdbm_plan_create().  The O(N)
+// passes are OpenMP-parallel (FVDBM_PLAN_THREADS, default omp_get_max_threads()).
 //
 // Device layout produced here (DESIGN.md "Data layout in HBM"):
 //   * cells live at "positions" pos[i] in [0,Npad); positions are grouped
@@ -13,18 +14,24 @@
 //       ccode: interior  (nbr_pos<<2) | (sign<0)<<1 | slot        slot = stencil slot of THIS cell
 //              boundary  -(((bside<<2) | (sign<0)<<1 | slot) + 1)
 //              hole      INT32_MIN in k=0 (padding position, skipped)
-//       ccoef: NC reals per side: m = n*L (2), and for Lax-Wendroff alpha = d0/(d0+d1),
-//              gamma = 1/(2 (d0+d1) L)   (src/containers.py:266-277 with varpi*L folded into m)
+//       ccoef: NC reals per side, in CELL orientation (sigma = sign entry, varsigma = +1 in slot 0, -1 in
+//              slot 1; sign folds are exact): M = sigma n L [inv_area] (2), and for Lax-Wendroff
+//              A = varsigma d0/(d0+d1), G = sigma varsigma /(2 (d0+d1) L [inv_area])
+//              (src/containers.py:266-277; core.cuh: side_flux)
 //   * boundary sides: the two tracked-node ids of the face and ratio d_ghost/d_known
 //     (src/containers.py:280-287, utils/utils.py:153-154)
-//   * tracked nodes (type != 0, or on a face with a ghost slot): compact ids, ring CSR with weights
+//   * tracked nodes (type 1/2, or on a face with a ghost slot): compact ids, ring CSR with weights
 //     w = 1/d, negative -> 0 (utils/utils.py:58-59), zero-weight entries dropped.
 #pragma once
 #include <cstdint>
 #include <climits>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <algorithm>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 #include "../../include/fvdbm_b200.h"
 
 namespace fvdbm {
@@ -32,31 +39,33 @@ namespace fvdbm {
 constexpr int TW = 32;            // lanes of one AoSoA mini-tile
 constexpr int PAD_TO = 512;       // group alignment = largest CTA tile
 constexpr int32_t HOLE = INT32_MIN;
-constexpr int BORDER_TILE = 256;  // cells per CTA of the border kernel
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+inline int plan_threads() {
+    int n = 1;
+#if defined(_OPENMP)
+    n = omp_get_max_threads();
+#endif
+    if (const char* e = getenv("FVDBM_PLAN_THREADS")) n = atoi(e);
+    return n < 1 ? 1 : n;
+}
 
 template <typename real>
 struct Plan {
     int64_t N = 0, F = 0, P = 0, No = 0;
     int Q = 9, K = 3, M = 0, scheme = 0, NC = 2;
-    int64_t Npad = 0, Bstart = 0, Oend = 0, Hstart = 0, D1start = 0;
-    std::vector<int32_t> l2_list;               // positions of the level-2 cells (inside the tiled group)
+    int64_t Npad = 0, Bstart = 0, Oend = 0, Hstart = 0;
     std::vector<int32_t> pos, ipos;
     bool fused_ok = true;
     std::string why_not;
-    std::vector<int32_t> ccode, cface;          // side codes; side -> shared face record (face layout)
-    std::vector<real> ccoef, fcoef;             // per-side coefficients (cell layout) / per-face records [NF][NC]
-    int64_t NF = 0;                             // face records referenced by owned cells
+    std::vector<int32_t> ccode;                 // side codes
+    std::vector<real> ccoef;                    // per-side coefficients, tiled like the codes
     int64_t NB = 0;
     std::vector<int32_t> bf_na, bf_nb;
     std::vector<real> bf_ratio;
-    int64_t NT = 0, NTpad = 0, NA = 0, NO = 0;  // tracked nodes; [0,NA) active (type != 0); [0,NO) active "orphans"
-                                                // not on any owned boundary side (only those need k_nodes when fused)
-    // border tiles (BORDER_TILE cells each, from Bstart): the tracked nodes each tile's boundary sides use
-    std::vector<int32_t> bt_off, bt_nodes, bf_la, bf_lb;
-    int64_t max_tile_nodes = 0;
-    std::vector<int32_t> tn_orig, tn_type, node_track, tn_active, ring_off, ring_cell;
+    int64_t NT = 0, NTpad = 0, NA = 0;          // tracked nodes; [0,NA) active (type 1 or 2)
+    std::vector<int32_t> tn_orig, tn_type, node_track, ring_off, ring_cell;
     std::vector<real> ring_w, tn_pdf, tn_rho, tn_vel;
     // the same rings as a fixed-width table [NA][MR] (zero weight = unused slot): lets the node kernel index
     // its ring entries directly instead of first loading CSR offsets (one dependent memory level less)
@@ -64,79 +73,10 @@ struct Plan {
     std::vector<real> ring_fw;
     int64_t MR = 0;
     std::vector<int32_t> s_cface, s_csign, s_fcell, s_fnode;
+    std::vector<real> s_inv_area;               // staged path: optional 1/area per position (empty = 1)
     std::string error;
 
     bool fail(const std::string& msg) { error = msg; return false; }
-
-    // ---- temporal blocking (two iterations per pass) -------------------------------------------------
-    // Tiles of T2 consecutive positions over [0, D1start) (cells at level >= 2).  Entry list of a tile:
-    //   [ own (T2, implicit positions) | ring1 = face neighbours of own | ring2 = face neighbours of ring1 ]
-    // The kernel stages the time-t populations of all entries in shared memory, advances own+ring1 to
-    // t+1 there (ring1 redundantly: neighbouring tiles do the same, identically), then own to t+2.
-    // t2_lnbr[entry][k] = (local id of the side's other cell << 2) | (sign<0)<<1 | slot, 16 bit.
-    static constexpr int T2 = 256;
-    std::vector<int32_t> t2_off, t2_n1, t2_pos;     // per tile: offset into t2_pos, #ring1; ring positions
-    std::vector<int64_t> t2_loff;                   // per tile: offset (in entries) into t2_lnbr
-    std::vector<uint16_t> t2_lnbr;
-    int64_t t2_tiles = 0, t2_max_entries = 0, t2_max_n01 = 0;
-    bool t2_ok = false;
-
-    void build_temporal_tiles(const fvdbm_desc& d, const std::vector<int32_t>& other, const std::vector<uint8_t>& slot) {
-        t2_ok = false;
-        t2_tiles = D1start / T2;
-        if (t2_tiles == 0) return;
-        t2_off.assign(t2_tiles + 1, 0); t2_n1.assign(t2_tiles, 0); t2_loff.assign(t2_tiles + 1, 0);
-        t2_pos.clear(); t2_lnbr.clear();
-        std::vector<int32_t> stamp(Npad, -1), lid(Npad, 0);
-        std::vector<int32_t> ring;
-        for (int64_t t = 0; t < t2_tiles; ++t) {
-            const int64_t t0 = t * T2;
-            ring.clear();
-            for (int e = 0; e < T2; ++e) { stamp[t0 + e] = (int32_t)t; lid[t0 + e] = e; }
-            // collect a ring (unstamped face neighbours of the given entries), sort it by position so that
-            // consecutive threads gather consecutive positions (shared 32 B sectors), then assign local ids
-            auto grow = [&](int64_t from_begin, int64_t from_end, bool from_own) {
-                const size_t first = ring.size();
-                for (int64_t e = from_begin; e < from_end; ++e) {
-                    const int64_t pc = from_own ? t0 + e : ring[e];
-                    const int64_t c = ipos[pc];
-                    if (c < 0 || c >= No) continue;
-                    for (int k = 0; k < K; ++k) {
-                        const int32_t o = other[c * K + k];
-                        if (o < 0) continue;                    // cannot happen for level >= 1 cells
-                        const int64_t np = pos[o];
-                        if (stamp[np] != (int32_t)t) { stamp[np] = (int32_t)t; ring.push_back((int32_t)np); }
-                    }
-                }
-                std::sort(ring.begin() + first, ring.end());
-                for (size_t i = first; i < ring.size(); ++i) lid[ring[i]] = (int32_t)(T2 + i);
-            };
-            grow(0, T2, true);
-            const int64_t n1 = (int64_t)ring.size();
-            grow(0, n1, false);
-            const int64_t n2 = (int64_t)ring.size() - n1;
-            t2_n1[t] = (int32_t)n1;
-            t2_off[t + 1] = t2_off[t] + (int32_t)ring.size();
-            t2_pos.insert(t2_pos.end(), ring.begin(), ring.end());
-            t2_loff[t + 1] = t2_loff[t] + (T2 + n1);
-            for (int64_t e = 0; e < T2 + n1; ++e) {
-                const int64_t pc = e < T2 ? t0 + e : ring[e - T2];
-                const int64_t c = ipos[pc];
-                for (int k = 0; k < K; ++k) {
-                    uint16_t v = 0xFFFF;                        // hole (padding position): skipped by the kernel
-                    if (c >= 0 && c < No) {
-                        const int32_t o = other[c * K + k];
-                        const int neg = d.cell_face_sign[c * K + k] < 0 ? 1 : 0;
-                        v = (uint16_t)((lid[pos[o]] << 2) | (neg << 1) | slot[c * K + k]);
-                    }
-                    t2_lnbr.push_back(v);
-                }
-            }
-            t2_max_entries = std::max<int64_t>(t2_max_entries, T2 + n1 + n2);
-            t2_max_n01 = std::max<int64_t>(t2_max_n01, T2 + n1);
-        }
-        t2_ok = t2_max_entries < (1 << 14);
-    }
 
     bool build(const fvdbm_desc& d) {
         N = d.N; F = d.F; P = d.P; Q = d.Q; K = d.K; M = d.M; scheme = d.scheme;
@@ -153,36 +93,62 @@ struct Plan {
             return fail("missing static array");
         if (P > 0 && (!d.node_type || !d.node_pdf || !d.node_rho || !d.node_vel)) return fail("missing node array");
         if (P > 0 && M > 0 && (!d.node_cell_idx || !d.node_cell_dist)) return fail("missing node ring arrays");
+        for (int q = 0; q < Q; ++q) {      // core.cuh evaluates W per weight class
+            const int cls = q == 0 ? 0 : q <= 4 ? 1 : q <= 8 ? 5 : 9;
+            if (d.lat_w[q] != d.lat_w[cls]) return fail("lattice weights must be constant on {0},{1..4},{5..8},{9..12}");
+        }
         const real* fdist = static_cast<const real*>(d.face_dists);
         const real* fn = static_cast<const real*>(d.face_n);
         const real* fL = static_cast<const real*>(d.face_L);
+        const real* inv_area = static_cast<const real*>(d.cell_inv_area);     // optional, NULL = reference (no area)
+        const int nthreads = plan_threads();
+        (void)nthreads;
 
         // ---- range checks -------------------------------------------------------------------
-        for (int64_t i = 0; i < No * K; ++i)      // halo cells carry no sides (never updated)
-            if (d.cell_face_idx[i] < 0 || d.cell_face_idx[i] >= F)
-                return fail("cell_face_idx out of range (ragged / -1 padded cells are not supported)");
-        for (int64_t i = 0; i < F * 2; ++i)
-            if (d.face_cell_idx[i] < -1 || d.face_cell_idx[i] >= N) return fail("face_cell_idx out of range");
+        {
+            int bad_cell = 0, bad_face = 0, bad_type = 0;
+#pragma omp parallel for num_threads(nthreads) reduction(| : bad_cell)
+            for (int64_t i = 0; i < No * K; ++i)      // halo cells carry no sides (never updated)
+                if (d.cell_face_idx[i] < 0 || d.cell_face_idx[i] >= F) bad_cell |= 1;
+#pragma omp parallel for num_threads(nthreads) reduction(| : bad_face)
+            for (int64_t i = 0; i < F * 2; ++i)
+                if (d.face_cell_idx[i] < -1 || d.face_cell_idx[i] >= N) bad_face |= 1;
+            for (int64_t n = 0; n < P; ++n)
+                if (d.node_type[n] < 0 || d.node_type[n] > 2) bad_type |= 1;
+            if (bad_cell) return fail("cell_face_idx out of range (ragged / -1 padded cells are not supported)");
+            if (bad_face) return fail("face_cell_idx out of range");
+            if (bad_type) return fail("node_type must be 0 (none), 1 (velocity) or 2 (density)");   // containers.py:339-351
+        }
 
         // ---- side analysis in original numbering -----------------------------------------------
         // other[i*K+k] = neighbour cell (>=0), -1 boundary, -2 inconsistent
-        std::vector<int32_t> other(N * K, -2);
-        std::vector<uint8_t> slot(N * K, 0);
+        std::vector<int32_t> other((size_t)N * K, -2);
+        std::vector<uint8_t> slot((size_t)N * K, 0);
         fused_ok = true;
-        for (int64_t c = 0; c < No && fused_ok; ++c)
-            for (int k = 0; k < K; ++k) {
-                int64_t j = d.cell_face_idx[c * K + k];
-                int32_t a = d.face_cell_idx[2 * j], b = d.face_cell_idx[2 * j + 1];
-                int32_t s = d.cell_face_sign[c * K + k];
-                if (s != 1 && s != -1) { fused_ok = false; why_not = "cell_face_sign not +-1"; break; }
-                if (a == c && b != c) { slot[c * K + k] = 0; other[c * K + k] = b; }
-                else if (b == c && a != c) { slot[c * K + k] = 1; other[c * K + k] = a; }
-                else { fused_ok = false; why_not = "a cell lists a face whose stencil does not contain it exactly once"; break; }
-                if (other[c * K + k] == -1) {
-                    int32_t na = d.face_node_idx[2 * j], nb = d.face_node_idx[2 * j + 1];
-                    if (na < 0 || na >= P || nb < 0 || nb >= P) { fused_ok = false; why_not = "boundary face without valid nodes"; break; }
+        {
+            int why = 0;      // 3: sign not +-1, 2: stencil does not contain the cell once, 1: boundary face without nodes
+#pragma omp parallel for num_threads(nthreads) reduction(max : why)
+            for (int64_t c = 0; c < No; ++c)
+                for (int k = 0; k < K; ++k) {
+                    const int64_t j = d.cell_face_idx[c * K + k];
+                    const int32_t a = d.face_cell_idx[2 * j], b = d.face_cell_idx[2 * j + 1];
+                    const int32_t s = d.cell_face_sign[c * K + k];
+                    if (s != 1 && s != -1) { why = std::max(why, 3); continue; }
+                    if (a == c && b != c) { slot[c * K + k] = 0; other[c * K + k] = b; }
+                    else if (b == c && a != c) { slot[c * K + k] = 1; other[c * K + k] = a; }
+                    else { why = std::max(why, 2); continue; }
+                    if (other[c * K + k] == -1) {
+                        const int32_t na = d.face_node_idx[2 * j], nb = d.face_node_idx[2 * j + 1];
+                        if (na < 0 || na >= P || nb < 0 || nb >= P) why = std::max(why, 1);
+                    }
                 }
+            if (why) {
+                fused_ok = false;
+                why_not = why == 3 ? "cell_face_sign not +-1"
+                        : why == 2 ? "a cell lists a face whose stencil does not contain it exactly once"
+                                   : "boundary face without valid nodes";
             }
+        }
 
         // ---- positions ------------------------------------------------------------------------
         std::vector<int32_t> order(N);               // rank -> original cell
@@ -204,34 +170,16 @@ struct Plan {
             // interior = owned cells whose K sides are all interior faces to owned cells: they need neither
             // node values nor halo copies, so the engine updates them concurrently with the exchange /
             // node kernel / border update (api.cu: step_fused_once).
-            // level = face-graph distance to the nearest border cell, capped at 3.  Positions are grouped
-            // [level>=2 | level 1 | level 0 = border]: the single-step schedule uses interior = [0,Bstart);
-            // the two-step temporal schedule tiles [0,D1start) and runs thin single-step passes over
-            // [D1start,end) plus the explicit list of level-2 cells (l2_list), which stay in locality order
-            // inside the tiled group so that no tile is a thin strip with a huge ring.
-            std::vector<uint8_t> lvl(N, 3);
+            std::vector<uint8_t> border(N, 0);
+#pragma omp parallel for num_threads(nthreads)
             for (int64_t c = 0; c < No; ++c)
                 for (int k = 0; k < K; ++k) {
-                    int32_t o = other[c * K + k];
-                    if (o == -1 || o >= No) lvl[c] = 0;
+                    const int32_t o = other[c * K + k];
+                    if (o == -1 || o >= No) border[c] = 1;
                 }
-            for (int L = 0; L < 2; ++L)
-                for (int64_t c = 0; c < No; ++c)
-                    if (lvl[c] == L)
-                        for (int k = 0; k < K; ++k) {
-                            int32_t o = other[c * K + k];
-                            if (o >= 0 && o < No && lvl[o] > L + 1) lvl[o] = (uint8_t)(L + 1);
-                        }
-            l2_list.clear();
-            for (int64_t r = 0; r < No; ++r)
-                if (lvl[order[r]] >= 2) {
-                    if (lvl[order[r]] == 2) l2_list.push_back((int32_t)p);
-                    pos[order[r]] = (int32_t)p++;
-                }
-            D1start = round_up(p, PAD_TO); p = D1start;
-            for (int64_t r = 0; r < No; ++r) if (lvl[order[r]] == 1) pos[order[r]] = (int32_t)p++;
+            for (int64_t r = 0; r < No; ++r) if (!border[order[r]]) pos[order[r]] = (int32_t)p++;
             Bstart = round_up(p, PAD_TO); p = Bstart;
-            for (int64_t r = 0; r < No; ++r) if (lvl[order[r]] == 0) pos[order[r]] = (int32_t)p++;
+            for (int64_t r = 0; r < No; ++r) if (border[order[r]]) pos[order[r]] = (int32_t)p++;
             Oend = p; Hstart = round_up(p, PAD_TO); p = Hstart;
             for (int64_t r = No; r < N; ++r) pos[order[r]] = (int32_t)p++;
         } else {
@@ -241,6 +189,7 @@ struct Plan {
         }
         Npad = round_up(std::max<int64_t>(p, 1), PAD_TO);
         ipos.assign(Npad, -1);
+#pragma omp parallel for num_threads(nthreads)
         for (int64_t i = 0; i < N; ++i) ipos[pos[i]] = (int32_t)i;
 
         // ---- tracked nodes --------------------------------------------------------------------
@@ -253,28 +202,17 @@ struct Plan {
                     int32_t n = d.face_node_idx[2 * j + e];
                     if (n >= 0 && n < P) want[n] = 1;
                 }
-        // order: active orphans | active nodes on an owned boundary side (evaluated by the border kernel,
-        // tile by tile) | inactive tracked nodes (keep their stored PDFs)
-        std::vector<uint8_t> on_side(P, 0);
-        if (fused_ok)
-            for (int64_t c = 0; c < No; ++c)
-                for (int k = 0; k < K; ++k)
-                    if (other[c * K + k] == -1) {
-                        const int64_t j = d.cell_face_idx[c * K + k];
-                        on_side[d.face_node_idx[2 * j]] = 1; on_side[d.face_node_idx[2 * j + 1]] = 1;
-                    }
-        tn_orig.clear(); tn_type.clear(); NA = 0; NO = 0;
-        for (int pass = 0; pass < 3; ++pass)
+        // order: active nodes (type 1 / 2, re-evaluated every step) | inactive tracked nodes (keep their PDFs)
+        tn_orig.clear(); tn_type.clear(); NA = 0;
+        for (int pass = 0; pass < 2; ++pass)
             for (int64_t n = 0; n < P; ++n) {
                 if (!want[n]) continue;
                 const bool active = d.node_type[n] != 0;
-                const int cls = !active ? 2 : (on_side[n] ? 1 : 0);
-                if (cls != pass) continue;
+                if ((active ? 0 : 1) != pass) continue;
                 node_track[n] = (int32_t)tn_orig.size();
                 tn_orig.push_back((int32_t)n);
                 tn_type.push_back(d.node_type[n]);
                 if (active) ++NA;
-                if (cls == 0) ++NO;
             }
         NT = (int64_t)tn_orig.size();
         NTpad = round_up(std::max<int64_t>(NT, 1), TW);
@@ -321,12 +259,19 @@ struct Plan {
         // ---- staged statics (general path + observables) ---------------------------------------
         s_cface.assign((size_t)K * Npad, 0);
         s_csign.assign((size_t)K * Npad, 0);
+#pragma omp parallel for num_threads(nthreads)
         for (int64_t c = 0; c < No; ++c)
             for (int k = 0; k < K; ++k) {
                 s_cface[(size_t)k * Npad + pos[c]] = d.cell_face_idx[c * K + k];
                 s_csign[(size_t)k * Npad + pos[c]] = d.cell_face_sign[c * K + k];
             }
+        s_inv_area.clear();
+        if (inv_area) {
+            s_inv_area.assign(Npad, real(1));
+            for (int64_t c = 0; c < No; ++c) s_inv_area[pos[c]] = inv_area[c];
+        }
         s_fcell.resize(2 * F); s_fnode.resize(2 * F);
+#pragma omp parallel for num_threads(nthreads)
         for (int64_t j = 0; j < F; ++j) {
             bool ghost = d.face_cell_idx[2 * j] == -1 || d.face_cell_idx[2 * j + 1] == -1;
             for (int e = 0; e < 2; ++e) {
@@ -343,29 +288,24 @@ struct Plan {
             const int64_t ntile = Npad / TW;
             ccode.assign((size_t)ntile * K * TW, 0);
             ccoef.assign((size_t)ntile * K * NC * TW, real(0));
-            for (int64_t q = 0; q < Npad; ++q)
-                if (ipos[q] < 0 || ipos[q] >= No) ccode[(size_t)(q >> 5) * K * TW + (q & 31)] = HOLE;
-            // two interchangeable coefficient layouts:
-            //   cell layout: ccoef[tile][k*NC+i][lane]   (perfectly coalesced, interior faces stored twice)
-            //   face layout: fcoef[rec][NC] + cface[tile][k][lane] -> rec (one 16 B record per face, shared by
-            //                both cells; records numbered by first touch in position order for locality)
-            cface.assign((size_t)ntile * K * TW, 0);
-            const int64_t nbt = (round_up(Oend, PAD_TO) - Bstart) / BORDER_TILE;
-            bt_off.assign(nbt + 1, 0); bt_nodes.clear(); bf_la.clear(); bf_lb.clear(); max_tile_nodes = 0;
-            std::vector<int32_t> slot_of(std::max<int64_t>(NT, 1), -1), stamp(std::max<int64_t>(NT, 1), -1);
-            int64_t cur_bt = -1;
-            auto tile_slot = [&](int64_t bt, int32_t t) -> int32_t {   // slot of tracked node t in border tile bt
-                while (cur_bt < bt) { ++cur_bt; bt_off[cur_bt] = (int32_t)bt_nodes.size(); }
-                if (stamp[t] != (int32_t)bt) { stamp[t] = (int32_t)bt; slot_of[t] = (int32_t)(bt_nodes.size() - bt_off[bt]); bt_nodes.push_back(t); }
-                return slot_of[t];
-            };
-            std::vector<int32_t> rec_of(F, -1);
-            fcoef.clear();
-            NF = 0;
+            // boundary sides are numbered in position order; they only occur in the border group
+            std::vector<int32_t> bside_base(std::max<int64_t>(Oend - Bstart, 0) + 1, 0);
+            for (int64_t pc = Bstart; pc < Oend; ++pc) {
+                const int64_t c = ipos[pc];
+                int nb = 0;
+                for (int k = 0; k < K; ++k) nb += other[c * K + k] == -1;
+                bside_base[pc - Bstart + 1] = bside_base[pc - Bstart] + nb;
+            }
+            NB = bside_base[std::max<int64_t>(Oend - Bstart, 0)];
+            if (NB >= (int64_t(1) << 28)) return fail("too many boundary sides");
+            bf_na.assign(NB, 0); bf_nb.assign(NB, 0); bf_ratio.assign(NB, real(0));
+#pragma omp parallel for num_threads(nthreads) schedule(static)
             for (int64_t pc = 0; pc < Npad; ++pc) {
                 const int64_t c = ipos[pc];
-                if (c < 0 || c >= No) continue;
                 const int64_t tile = pc >> 5, lane = pc & 31;
+                if (c < 0 || c >= No) { ccode[(size_t)(tile * K) * TW + lane] = HOLE; continue; }
+                int64_t nb = pc >= Bstart ? bside_base[pc - Bstart] : 0;
+                const real ia = inv_area ? inv_area[c] : real(1);
                 for (int k = 0; k < K; ++k) {
                     const int64_t j = d.cell_face_idx[c * K + k];
                     const int sl = slot[c * K + k];
@@ -375,38 +315,27 @@ struct Plan {
                     if (o >= 0) code = (pos[o] << 2) | (neg << 1) | sl;
                     else {
                         const real dg = fdist[2 * j + (1 - sl)], dk = fdist[2 * j + sl];
-                        const int32_t ta = node_track[d.face_node_idx[2 * j]], tb = node_track[d.face_node_idx[2 * j + 1]];
-                        bf_na.push_back(ta);
-                        bf_nb.push_back(tb);
-                        bf_ratio.push_back(dg / dk);
-                        const int64_t bt = (pc - Bstart) / BORDER_TILE;       // boundary cells live in the border group
-                        bf_la.push_back(tile_slot(bt, ta));
-                        bf_lb.push_back(tile_slot(bt, tb));
-                        code = -(int32_t)(((NB << 2) | (neg << 1) | sl) + 1);
-                        ++NB;
+                        bf_na[nb] = node_track[d.face_node_idx[2 * j]];
+                        bf_nb[nb] = node_track[d.face_node_idx[2 * j + 1]];
+                        bf_ratio[nb] = dg / dk;
+                        code = -(int32_t)(((nb << 2) | (neg << 1) | sl) + 1);
+                        ++nb;
                     }
                     ccode[(size_t)(tile * K + k) * TW + lane] = code;
+                    const real sg = neg ? real(-1) : real(1), vs = sl ? real(-1) : real(1);
                     real co[4] = {0, 0, 0, 0};
-                    const real L = fL[j];
-                    co[0] = fn[2 * j] * L;
-                    co[1] = fn[2 * j + 1] * L;
+                    real L = fL[j];
+                    if (inv_area) L = L * ia;
+                    co[0] = sg * (fn[2 * j] * L);
+                    co[1] = sg * (fn[2 * j + 1] * L);
                     if (NC == 4) {
                         const real d0 = fdist[2 * j], d1 = fdist[2 * j + 1], dd = d0 + d1;
-                        co[2] = d0 / dd;
-                        co[3] = real(1) / (real(2) * dd * L);
+                        co[2] = vs * (d0 / dd);
+                        co[3] = (sg * vs) * (real(1) / (real(2) * dd * L));
                     }
                     for (int i = 0; i < NC; ++i) ccoef[(size_t)((tile * K + k) * NC + i) * TW + lane] = co[i];
-                    if (rec_of[j] < 0) {
-                        rec_of[j] = (int32_t)NF++;
-                        for (int i = 0; i < NC; ++i) fcoef.push_back(co[i]);
-                    }
-                    cface[(size_t)(tile * K + k) * TW + lane] = rec_of[j];
                 }
             }
-            while (cur_bt < nbt) { ++cur_bt; bt_off[cur_bt] = (int32_t)bt_nodes.size(); }
-            for (int64_t t = 0; t < nbt; ++t) max_tile_nodes = std::max<int64_t>(max_tile_nodes, bt_off[t + 1] - bt_off[t]);
-            if (NB >= (int64_t(1) << 28)) return fail("too many boundary sides");
-            if (!has_halo) build_temporal_tiles(d, other, slot);
         }
         return true;
     }

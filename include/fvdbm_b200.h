@@ -18,6 +18,7 @@
  *   node_cell_idx  [P*M] i32   Nodes.cells_index (-1 pad)   src/containers.py:306
  *   node_cell_dist [P*M] real  Nodes.cell_dists  (-1 pad)   src/containers.py:307
  *   cell_pdf [N*Q], node_pdf [P*Q], node_rho [P], node_vel [P*2]  initial dynamic state
+ * node_type values other than 0/1/2 are rejected (the reference updates only types 1 and 2).
  * `real` is float when dtype==32 and double when dtype==64.
  *
  * Threading: one handle = one device + one CUDA stream; calls on a handle are not thread-safe,
@@ -35,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FVDBM_ABI_VERSION 1
+#define FVDBM_ABI_VERSION 2   /* 2: fvdbm_desc.cell_inv_area, FVDBM_VARIANT_PAIR; temporal blocking removed */
 
 /* status codes */
 #define FVDBM_OK              0
@@ -54,9 +55,16 @@ extern "C" {
 #define FVDBM_MODE_FUSED  2   /* node kernel + one cell-centric kernel per step                   */
 
 /* fused-kernel variants (fvdbm_set_option(h, FVDBM_OPT_VARIANT, v)) */
-#define FVDBM_VARIANT_AUTO   0
+#define FVDBM_VARIANT_AUTO   0   /* fp32: PAIR, fp64: DIRECT                                   */
 #define FVDBM_VARIANT_DIRECT 1   /* thread per cell, all operands through L1/L2               */
 #define FVDBM_VARIANT_TMA    2   /* persistent CTAs, cp.async.bulk + mbarrier tile pipeline   */
+#define FVDBM_VARIANT_PAIR   3   /* fp32 only: two cells per thread, packed FFMA2 math, 64-bit
+                                    coalesced streaming accesses                              */
+/* All variants execute the same canonical operation sequence: results are bit-identical.
+ * Debug / A-B environment overrides read once at fvdbm_create (each mirrors an fvdbm_option):
+ *   FVDBM_VARIANT, FVDBM_TILE_CELLS, FVDBM_STAGES, FVDBM_GRAPH_STEPS, FVDBM_CTAS_PER_SM,
+ *   FVDBM_REVERSE_SWEEP, FVDBM_OVERLAP (0: no side stream for the interior cells),
+ *   FVDBM_PLAN_THREADS (host planner threads), FVDBM_NCCL_LIB (path of libnccl to dlopen). */
 
 /* fields for fvdbm_get / fvdbm_set (reference attribute in brackets) */
 enum fvdbm_field {
@@ -93,9 +101,8 @@ enum fvdbm_option {
     FVDBM_OPT_GRAPH_STEPS = 3,    /* steps captured per CUDA graph (0 = no graph)            */
     FVDBM_OPT_CTAS_PER_SM = 4,    /* persistent grid = 148 * this (0 = occupancy query)      */
     FVDBM_OPT_REVERSE_SWEEP = 5,  /* 1: odd steps sweep tiles backwards (L2 reuse of writes) */
-    FVDBM_OPT_TEMPORAL = 6        /* 1: temporal blocking -- two iterations per pass over overlapped tiles
-                                     (bit-identical results, about half the DRAM traffic per iteration);
-                                     single-GPU fused handles only */
+    FVDBM_OPT_TEMPORAL = 6        /* removed in ABI 2 (two-iterations-per-pass temporal blocking halved the DRAM
+                                     traffic but measured slower); 0 accepted, 1 -> ERR_UNSUPPORTED */
 };
 
 typedef struct fvdbm_handle fvdbm_handle;
@@ -133,6 +140,9 @@ typedef struct fvdbm_desc {
     const void*    node_vel;
     const int32_t* cell_perm;  /* optional [N]: storage position of original cell i (a bijection
                                   onto [0,N), must map owned cells onto [0,N_owned)); NULL = identity */
+    const void*    cell_inv_area; /* optional [N] real: 1/area of every cell, multiplying the flux divergence
+                                  (physically consistent update on non-unit cells).  NULL = the reference's
+                                  behaviour: no area anywhere (src/containers.py:115-121), i.e. parity mode */
 } fvdbm_desc;
 
 int  fvdbm_abi_version(void);

@@ -19,12 +19,15 @@ fb = pytest.importorskip("fvdbm_jax_b200")
 from fvdbm_jax_b200 import _lib, meshgen  # noqa: E402
 
 TOL = {np.float32: 1e-5, np.float64: 1e-11}
-MODES = {"tma": ("fused", _lib.VARIANT_TMA), "direct": ("fused", _lib.VARIANT_DIRECT), "staged": ("staged", None)}
+MODES = {"tma": ("fused", _lib.VARIANT_TMA), "direct": ("fused", _lib.VARIANT_DIRECT), "pair": ("fused", _lib.VARIANT_PAIR),
+         "staged": ("staged", None)}
 
 
 def make_env(case, dtype, mode, reorder="none"):
     cells, faces, nodes = case.containers()
     m, variant = MODES[mode]
+    if variant == _lib.VARIANT_PAIR and np.dtype(dtype) != np.float32:
+        pytest.skip("the packed pair kernel is fp32 only")
     env = fb.Environment(cells, faces, nodes, dtype=dtype, mode=m, reorder=reorder)
     env.init()
     if variant is not None:
@@ -43,7 +46,7 @@ def check_state(env, case, step, tol):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("mode", ["tma", "direct", "staged"])
+@pytest.mark.parametrize("mode", ["pair", "tma", "direct", "staged"])
 @pytest.mark.parametrize("name", golden.names())
 def test_golden_all_fields(name, mode, dtype):
     case = golden.Case(name)
@@ -56,7 +59,7 @@ def test_golden_all_fields(name, mode, dtype):
     env.close()
 
 
-@pytest.mark.parametrize("mode", ["direct", "tma", "staged"])
+@pytest.mark.parametrize("mode", ["pair", "direct", "tma", "staged"])
 @pytest.mark.parametrize("name", golden.names(fp32=True))
 def test_fp32_engine_vs_reference_run_in_fp32(name, mode):
     """*_f32 fixtures = the reference's own code executed with every float in fp32 (what stock JAX
@@ -118,19 +121,39 @@ def test_seeded_mesh_vs_oracle(dtype, steps, scheme):
     env.close()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["ldc_tri_lw", "channel_upwind", "channel_lw", "cylinder_lw", "quad_ldc_d2q13", "tri_d2q13_lw",
+                                  "pressure_lw_dm2"])
+def test_gpu_bits_equal_the_cpu_walk_of_the_same_operation_sequence(name, dtype):
+    """core.cuh spells out one canonical operation sequence (explicit add/mul/fma, fixed reduction order):
+    the CUDA kernels (packed pair kernel in fp32, thread-per-cell in fp64) must reproduce, bit for bit, the
+    g++ build of the same functions walking the same layout on the CPU (tests/hostsim)."""
+    import test_hostsim
+    case = golden.Case(name)
+    s = case.steps[-1]
+    cpu = test_hostsim.run(case, dtype, s)
+    cells, faces, nodes = case.containers()
+    env = fb.Environment(cells, faces, nodes, dtype=dtype, mode="fused", reorder="none")
+    env.init()
+    env = env.step(s)
+    for key in ("cells.pdf", "cells.rho", "cells.vel", "nodes.pdf", "nodes.rho", "nodes.vel"):
+        obj, attr = key.split(".")
+        np.testing.assert_array_equal(getattr(getattr(env, obj), attr), cpu[key], err_msg=f"{name} {key}")
+    env.close()
+
+
 def test_fused_variants_bitwise_identical():
     """direct / TMA (every tile size, pipeline depth, sweep direction, graph batching) and any
     renumbering run the same per-cell arithmetic -> bit-identical populations."""
     m, dyn, cells, faces, nodes = _square_problem(64, 48, periodic=True)
     ref = None
-    configs = [dict(variant=_lib.VARIANT_DIRECT), dict(variant=_lib.VARIANT_TMA, tile=128, stages=2),
+    configs = [dict(variant=_lib.VARIANT_DIRECT), dict(variant=_lib.VARIANT_PAIR), dict(variant=_lib.VARIANT_TMA, tile=128, stages=2),
                dict(variant=_lib.VARIANT_TMA, tile=256, stages=3), dict(variant=_lib.VARIANT_TMA, tile=512, stages=2),
                dict(variant=_lib.VARIANT_TMA, tile=256, stages=4, reverse=1, graph=4),
                dict(variant=_lib.VARIANT_DIRECT, reverse=1, graph=2, reorder="hilbert"),
                dict(variant=_lib.VARIANT_TMA, tile=128, stages=4, reorder="rcm", ctas=1)]
-    configs.append(dict(variant=_lib.VARIANT_DIRECT, border_fused=1))      # k_border experiment path stays correct
+    configs.append(dict(variant=_lib.VARIANT_PAIR, reverse=1, graph=6, reorder="rcm"))
     for cfg in configs:
-        os.environ["FVDBM_BORDER_FUSED"] = str(cfg.get("border_fused", 0))
         env = fb.Environment(cells, faces, nodes, dtype=np.float32, reorder=cfg.get("reorder", "none"))
         env.init()
         env.set_option(_lib.OPT_VARIANT, cfg["variant"])
@@ -146,40 +169,14 @@ def test_fused_variants_bitwise_identical():
             for a, b in zip(ref, got):
                 np.testing.assert_array_equal(a, b, err_msg=str(cfg))
         env.close()
-    os.environ.pop("FVDBM_BORDER_FUSED", None)
 
 
-@pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("scheme,periodic", [("lax_wendroff", False), ("upwind", True)])
-def test_temporal_blocking_is_bit_identical(scheme, periodic, dtype):
-    """FVDBM_OPT_TEMPORAL: two iterations per pass over overlapped tiles (k_fused2 + thin single-step
-    passes near the boundary) must give exactly the bits of the single-step schedule, for odd and even
-    step counts, including the lagged observables."""
-    m, dyn, cells, faces, nodes = _square_problem(90, 70, scheme, periodic=periodic)
-    outs = []
-    for temporal in (0, 1):
-        env = fb.Environment(cells, faces, nodes, dtype=dtype, reorder="hilbert")
-        env.init()
-        env.set_option(_lib.OPT_GRAPH_STEPS, 0)
-        env.set_option(_lib.OPT_TEMPORAL, temporal)
-        got = []
-        for n in (1, 2, 3, 8, 11):
-            env = env.step(n)
-            got.append((env.cells.pdf.copy(), env.cells.rho.copy(), env.cells.vel.copy(), env.nodes.pdf.copy(),
-                        env.faces.pdf.copy()))
-        outs.append(got)
-        env.close()
-    for a, b in zip(*outs):
-        for x, y in zip(a, b):
-            np.testing.assert_array_equal(x, y)
-
-
-def test_temporal_blocking_is_refused_where_it_cannot_apply():
+def test_removed_temporal_option_is_refused():
     case = golden.Case("ldc_tri_lw")
-    env = make_env(case, np.float32, "staged")
-    with pytest.raises(RuntimeError, match="temporal blocking"):
+    env = make_env(case, np.float32, "direct")
+    env.set_option(_lib.OPT_TEMPORAL, 0)
+    with pytest.raises(RuntimeError, match="temporal blocking was removed"):
         env.set_option(_lib.OPT_TEMPORAL, 1)
-        env.step(1)
     env.close()
 
 
@@ -291,7 +288,7 @@ def test_full_size_properties():
     rho_lag = env.cells.rho.copy()
     prev = np.empty((n, 9), np.float32)
     env.get_into("cells.pdf", prev)                     # current
-    assert env.info(_lib.INFO_VARIANT) == _lib.VARIANT_DIRECT          # the default kernel produced `a`
+    assert env.info(_lib.INFO_VARIANT) == _lib.VARIANT_PAIR            # the default fp32 kernel produced `a`
     for variant, reverse in ((_lib.VARIANT_TMA, 0), (_lib.VARIANT_DIRECT, 1)):
         env.set_option(_lib.OPT_VARIANT, variant).set_option(_lib.OPT_REVERSE_SWEEP, reverse)
         assert env.info(_lib.INFO_VARIANT) == variant

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/fvdbm_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert _lib.load().fvdbm_abi_version() == 1
+    assert _lib.load().fvdbm_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_desc_struct_matches_header_layout():
@@ -36,7 +36,7 @@ def test_desc_struct_matches_header_layout():
     for n in names:
         flat += [x.strip().split("[")[0].lstrip("*") for x in n.split(",")]
     assert flat == [f[0] for f in _lib.Desc._fields_]
-    assert C.sizeof(_lib.Desc) == 8 * 4 + 4 * 8 + 2 * 8 + 16 * 8 + 4 * 8 + 15 * 8
+    assert C.sizeof(_lib.Desc) == 8 * 4 + 4 * 8 + 2 * 8 + 16 * 8 + 4 * 8 + 16 * 8
 
 
 @pytest.mark.parametrize("name", ["cylinder_lw", "quad_ldc_d2q13", "channel_upwind"])
@@ -78,27 +78,24 @@ def test_host_plan_layout(name):
     want = set(np.nonzero(typ != 0)[0].tolist()) | set(case.static["faces.nodes_index"][ghost_faces].reshape(-1).tolist())
     tn = hp.array("tn_orig")
     assert set(tn.tolist()) == want and hp.scalar("NT") == len(want)
-    na, no = hp.scalar("NA"), hp.scalar("NO")
+    na = hp.scalar("NA")
     assert np.all(typ[tn[:na]] != 0) and np.all(typ[tn[na:]] == 0)
-    # border tiles: every boundary side finds its two nodes in its tile's node list; orphans (active
-    # nodes no owned boundary side references) come first and are in no tile list
-    bt_off, bt_nodes = hp.array("bt_off"), hp.array("bt_nodes")
-    bf_na, bf_nb, bf_la, bf_lb = (hp.array(k) for k in ("bf_na", "bf_nb", "bf_la", "bf_lb"))
+    # boundary sides are numbered in position order and carry the tracked ids of their face's two nodes
+    bf_na, bf_nb = hp.array("bf_na"), hp.array("bf_nb")
+    track = hp.array("node_track")
+    fnodes = case.static["faces.nodes_index"]
     b = 0
-    for p in range(Bstart, Npad):                       # boundary sides are numbered in position order
+    for p in range(Bstart, Npad):
         if ipos[p] < 0:
             continue
-        tile = (p - Bstart) // 256
         for k in range(K):
             cd = int(code[p >> 5, k, p & 31])
             if cd < 0 and cd != np.iinfo(np.int32).min:
                 assert (-(cd + 1)) >> 2 == b
-                lst = bt_nodes[bt_off[tile]:bt_off[tile + 1]]
-                assert lst[bf_la[b]] == bf_na[b] and lst[bf_lb[b]] == bf_nb[b]
+                j = fi[ipos[p], k]
+                assert bf_na[b] == track[fnodes[j, 0]] and bf_nb[b] == track[fnodes[j, 1]]
                 b += 1
     assert b == hp.scalar("NB")
-    assert hp.scalar("max_tile_nodes") == int(np.max(np.diff(bt_off))) if bt_off.size > 1 else True
-    assert not (set(range(no)) & set(bt_nodes.tolist()))
     hp.close()
 
 

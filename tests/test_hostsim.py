@@ -63,37 +63,3 @@ def test_hostsim_permutation_invariance(name):
     b = run(case, np.float64, s, perm=perm)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k])     # same arithmetic per cell -> bitwise equal
-
-
-def _square_desc(nx, ny, scheme, dtype, periodic):
-    import fvdbm_jax_b200 as fb
-    from fvdbm_jax_b200 import meshgen
-    raw = meshgen.triangulated_square(nx, ny, seed=11, periodic_x=periodic)
-    m = fb.Mesher()
-    m.import_meshpy(raw)
-    m.calc_mesh_properties()
-    dyn = fb.D2Q9(0.8, 0.1)
-    cells, faces, nodes = m.to_env(dyn, scheme)
-    for mk in ((1,) if periodic else (1, 2, 4)):
-        nodes = m.set_vel_node(nodes, mk, np.array([0.0, 0.0]))
-    nodes = m.set_vel_node(nodes, 3, np.array([0.1, 0.0]))
-    c = m.cell_centers
-    cells.pdf = dyn.calc_eq(1 + 0.01 * np.sin(2 * np.pi * c[:, 0] / nx) * np.sin(2 * np.pi * c[:, 1] / ny),
-                            0.05 * np.stack([np.sin(2 * np.pi * c[:, 1] / ny), np.sin(2 * np.pi * c[:, 0] / nx)], axis=1))
-    return fb.Environment(cells, faces, nodes, dtype=dtype, reorder="hilbert")._describe()
-
-
-@pytest.mark.parametrize("nx,ny,scheme,dtype,periodic", [(40, 30, "lax_wendroff", np.float64, False),
-                                                         (64, 48, "upwind", np.float32, True)])
-def test_temporal_tiles_equal_two_single_steps(nx, ny, scheme, dtype, periodic):
-    """Planner (levels, rings, local ids) + the two-iterations-per-pass schedule of api.cu::superstep /
-    k_fused2, mirrored on the CPU: bit-identical to the single-step walk."""
-    da = _square_desc(nx, ny, scheme, dtype, periodic)
-    real = np.dtype(dtype)
-    a, b = np.zeros((da.N, da.Q), real), np.zeros((da.N, da.Q), real)
-    z = [np.zeros((da.P, da.Q), real), np.zeros(da.P, real), np.zeros((da.P, 2), real), np.zeros(da.N, real), np.zeros((da.N, 2), real)]
-    lib = hostsim()
-    lib.hostsim_run_temporal.restype = C.c_int
-    assert lib.hostsim_run(C.byref(da.desc), 6, C.c_void_p(a.ctypes.data), *[C.c_void_p(x.ctypes.data) for x in z]) == 0
-    assert lib.hostsim_run_temporal(C.byref(da.desc), 3, C.c_void_p(b.ctypes.data)) == 0, lib.hostsim_error().decode()
-    np.testing.assert_array_equal(a, b)

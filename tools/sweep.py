@@ -18,7 +18,6 @@ def main():
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--reorders", default="hilbert,none,rcm")
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--temporal", action="store_true", help="A/B the two-iterations-per-pass schedule")
     args = ap.parse_args()
     real = np.float32 if args.dtype == "f32" else np.float64
     m, dyn, cells, faces, nodes, t_mesh = bench.build_problem(args.nx, args.nx, args.scheme)
@@ -27,7 +26,7 @@ def main():
     b_alg = per_cell + per_face * faces.n.shape[0] / n
     peak, _ = bench.measured_peak()
     print(json.dumps({"cells": n, "mesh_s": t_mesh, "b_alg": b_alg}), flush=True)
-    cfgs = [dict(variant=1)]
+    cfgs = [dict(variant=3), dict(variant=1)]
     for tile in (128, 256, 512):
         for stages in (2, 3, 4):
             cfgs.append(dict(variant=2, tile=tile, stages=stages))
@@ -36,9 +35,7 @@ def main():
              dict(variant=2, tile=128, stages=4, ctas=4), dict(variant=2, tile=256, stages=3, graph=10),
              dict(variant=2, tile=256, stages=3, reverse=1, graph=10)]
     if args.quick:
-        cfgs = [dict(variant=1), dict(variant=2, tile=256, stages=3), dict(variant=2, tile=256, stages=3, reverse=1)]
-    if args.temporal:
-        cfgs = [dict(variant=1), dict(variant=1, temporal=1)]
+        cfgs = [dict(variant=3), dict(variant=1), dict(variant=2, tile=256, stages=3)]
     for reorder in args.reorders.split(","):
         t0 = time.time()
         if reorder == "random":       # worst case: what an arbitrarily numbered unstructured mesh looks like
@@ -48,12 +45,13 @@ def main():
         env = fb.Environment(cells, faces, nodes, dtype=real, reorder=reorder_arg)
         env.init(); env.build()
         t_build = time.time() - t0
-        for cfg in (cfgs if (reorder == "hilbert" or args.temporal) else cfgs[:1] + [c for c in cfgs if c.get("variant") == 2 and c.get("tile") == 256 and c.get("stages") == 3][:2]):
+        for cfg in (cfgs if reorder == "hilbert" else cfgs[:2] + [c for c in cfgs if c.get("variant") == 2 and c.get("tile") == 256 and c.get("stages") == 3][:2]):
+            if cfg["variant"] == 3 and real is np.float64:
+                continue
             env.set_option(_lib.OPT_VARIANT, cfg["variant"])
             env.set_option(_lib.OPT_TILE_CELLS, cfg.get("tile", 256)).set_option(_lib.OPT_STAGES, cfg.get("stages", 3))
             env.set_option(_lib.OPT_REVERSE_SWEEP, cfg.get("reverse", 0)).set_option(_lib.OPT_GRAPH_STEPS, cfg.get("graph", 0))
             env.set_option(_lib.OPT_CTAS_PER_SM, cfg.get("ctas", 0))
-            env.set_option(_lib.OPT_TEMPORAL, cfg.get("temporal", 0))
             env.step(10); env.sync()
             best = min(env.step_timed(args.inner) for _ in range(3))
             it_ms = best / args.inner
