@@ -129,6 +129,8 @@ struct EngineT final : Engine {
     int mode = FVDBM_MODE_FUSED;
     int variant = FVDBM_VARIANT_DIRECT;   // fp32: PAIR (two cells per thread, packed math); fp64: DIRECT; TMA is opt-in
     int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
+    int prefetch_dist = 296;             // CTAs of L2 look-ahead (0.4 of a resident wave); measured on B200: burst 0.231 -> 0.194 ms per
+                                         // 10M-cell iteration, sustained +2-3 % (profiles/r2_ab_pair_kernel.jsonl)
     int num_sms = 148;
     int cur = 0;
     int64_t steps = 0, launches = 0;
@@ -253,6 +255,7 @@ struct EngineT final : Engine {
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
+        if (const char* e = getenv("FVDBM_PREFETCH_DIST")) prefetch_dist = atoi(e);
         if (variant == FVDBM_VARIANT_AUTO) variant = default_variant();
         return sanitize_options();
     }
@@ -284,6 +287,7 @@ struct EngineT final : Engine {
         a.G.npdf = npdf.p; a.G.NTpad = plan.NTpad;
         a.cell_begin = begin; a.cell_end = end;
         a.reverse = (reverse_sweep && cur == 1) ? 1 : 0;
+        a.prefetch_dist = prefetch_dist;
         return a;
     }
 
@@ -333,7 +337,7 @@ struct EngineT final : Engine {
 
     // fp32 only: two cells per thread, 128 threads (= 256 cells) per CTA
     void launch_pair(const FusedArgs<float>& a, int64_t cells, cudaStream_t st) {
-        k_fused_pair<Q, K, SCHEME><<<blocks_for(cells / 2, 128), 128, 0, st>>>(a);
+        k_fused_pair<Q, K, SCHEME><<<blocks_for(cells / 2, FVDBM_PAIR_THREADS), FVDBM_PAIR_THREADS, 0, st>>>(a);
     }
     void launch_pair(const FusedArgs<double>&, int64_t, cudaStream_t) {}
 
@@ -695,6 +699,7 @@ struct EngineT final : Engine {
         case FVDBM_OPT_GRAPH_STEPS: graph_steps = (int)v; break;
         case FVDBM_OPT_CTAS_PER_SM: ctas_per_sm = (int)v; break;
         case FVDBM_OPT_REVERSE_SWEEP: reverse_sweep = v ? 1 : 0; break;
+        case FVDBM_OPT_PREFETCH_DIST: if (v < 0 || v > (1 << 20)) { err = "prefetch distance out of range"; return FVDBM_ERR_ARG; } prefetch_dist = (int)v; break;
         case FVDBM_OPT_TEMPORAL:
             if (v) { err = "temporal blocking was removed in ABI 2 (measured slower than the single-step kernel; DESIGN.md)"; return FVDBM_ERR_UNSUPPORTED; }
             break;

@@ -24,7 +24,32 @@ struct FusedArgs {
     GhostTables<real> G;               // boundary sides + tracked node populations
     int64_t cell_begin, cell_end;      // position range, multiples of PAD_TO (512)
     int reverse;                       // 1: sweep tiles from the top (L2 reuse of last step's writes)
+    int prefetch_dist;                 // >0: every CTA asks L2 to prefetch the streaming operands of the CTA
+                                       // `prefetch_dist` blocks ahead (cp.async.bulk.prefetch.L2)
 };
+
+#ifndef FVDBM_PAIR_THREADS
+#define FVDBM_PAIR_THREADS 128
+#endif
+#ifndef FVDBM_PAIR_MINCTAS
+#define FVDBM_PAIR_MINCTAS 5          // A/B on B200 (profiles/r2_ab_pair_kernel.jsonl): 128x5 (96 regs) beats 128x4, 128x6 (spills),
+#endif                                // 256x2 and 64x8 in both the burst and the power-capped sustained regime
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// The AoSoA layout makes the streaming operands of any run of `cells` consecutive positions three
+// contiguous blocks (populations, side coefficients, side codes): one bulk L2 prefetch each, issued by a
+// single thread, moves the DRAM latency of a later CTA's first loads off its warps.
+template <typename real, int Q, int K, int NC>
+__device__ __forceinline__ void prefetch_cells_l2(const FusedArgs<real>& a, int64_t first_cell, int cells) {
+    if (first_cell < a.cell_begin || first_cell + cells > a.cell_end) return;
+    const size_t mt = (size_t)(first_cell >> 5);
+    prefetch_l2_bulk(a.pdf_in + mt * (Q * kTW), (uint32_t)(cells * Q * sizeof(real)));
+    prefetch_l2_bulk(a.ccoef + mt * (K * NC * kTW), (uint32_t)(cells * K * NC * sizeof(real)));
+    prefetch_l2_bulk(a.ccode + mt * (K * kTW), (uint32_t)(cells * K * sizeof(int32_t)));
+}
 
 // measured on B200 (profiles/r1_experiment_occupancy_cachehints.txt): fp32 is best left to ptxas
 // (5 CTAs/SM; forcing 6 or 8 CTAs spills and loses 2-18 %), fp64 gains 15 % from 3 CTAs/SM.
@@ -39,6 +64,9 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     const int64_t nblk = gridDim.x;
     const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
     const int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
+    if (a.prefetch_dist > 0 && threadIdx.x == 0)
+        prefetch_cells_l2<real, Q, K, NC>(a, a.cell_begin + (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x,
+                                          (int)blockDim.x);
     if (c >= a.cell_end) return;
     const size_t tile = (size_t)(c >> 5);
     const int lane = (int)(c & 31);
@@ -86,11 +114,14 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
 // what was limiting it once the power cap pulls the SM clock down.
 // ------------------------------------------------------------------------------------------------
 template <int Q, int K, int SCHEME>
-__global__ void __launch_bounds__(128, 4) k_fused_pair(const FusedArgs<float> a) {
+__global__ void __launch_bounds__(FVDBM_PAIR_THREADS, FVDBM_PAIR_MINCTAS) k_fused_pair(const FusedArgs<float> a) {
     constexpr int NC = SCHEME == 0 ? 2 : 4;
     const int64_t nblk = gridDim.x;
     const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
     const int64_t c = a.cell_begin + 2 * (blk * blockDim.x + threadIdx.x);       // even position; pair (c, c+1)
+    if (a.prefetch_dist > 0 && threadIdx.x == 0)
+        prefetch_cells_l2<float, Q, K, NC>(a, a.cell_begin + 2 * (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x,
+                                           2 * (int)blockDim.x);
     if (c >= a.cell_end) return;
     const size_t tile = (size_t)(c >> 5);
     const int lane = (int)(c & 31);

@@ -101,6 +101,8 @@ enum fvdbm_option {
     FVDBM_OPT_GRAPH_STEPS = 3,    /* steps captured per CUDA graph (0 = no graph)            */
     FVDBM_OPT_CTAS_PER_SM = 4,    /* persistent grid = 148 * this (0 = occupancy query)      */
     FVDBM_OPT_REVERSE_SWEEP = 5,  /* 1: odd steps sweep tiles backwards (L2 reuse of writes) */
+    FVDBM_OPT_PREFETCH_DIST = 7,  /* >0: each CTA bulk-prefetches into L2 the streaming operands of the CTA this
+                                     many blocks ahead (direct / pair kernels); 0 = off                      */
     FVDBM_OPT_TEMPORAL = 6        /* removed in ABI 2 (two-iterations-per-pass temporal blocking halved the DRAM
                                      traffic but measured slower); 0 accepted, 1 -> ERR_UNSUPPORTED */
 };

@@ -174,6 +174,7 @@ def test_fused_variants_bitwise_identical():
 def test_removed_temporal_option_is_refused():
     case = golden.Case("ldc_tri_lw")
     env = make_env(case, np.float32, "direct")
+    env.build()
     env.set_option(_lib.OPT_TEMPORAL, 0)
     with pytest.raises(RuntimeError, match="temporal blocking was removed"):
         env.set_option(_lib.OPT_TEMPORAL, 1)
