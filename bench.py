@@ -372,12 +372,16 @@ def main():
                 "traffic": None, "kernel": {1: "k_fused_direct", 2: "k_fused_tma", 3: "k_fused_pair"}.get(n_launch_info, "?"),
                 "algorithmic_bytes_per_cell_update": b_alg, "cells_per_launch": n_local, "avg_launch_ms": iter_ms,
                 "peak_source": peak_src,
-                "note": "avg_launch_ms = event time / iterations (includes the O(sqrt N) node kernel); traffic from "
-                        "profiles/ ncu capture when available"}
+                "note": "avg_launch_ms = event time / iterations (includes the O(sqrt N) node + border launches that run "
+                        "concurrently); traffic = DRAM bytes of one launch from the committed ncu capture named in "
+                        "traffic_source, null when that capture is of another kernel / size"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof):          # one ncu --set full capture of the dominant kernel; says which commit it was taken at
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            t = json.load(open(prof))
+            if t.get("kernel", "").startswith(roofline["kernel"]) and t.get("cells_per_launch") == n_local:
+                roofline["traffic"] = t.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = f"{t.get('capture')} at commit {t.get('captured_at_commit')} (not re-measured in this run)"
         except Exception:
             pass
     line = {"metric": "MCUPS", "value": value, "unit": "MCUPS", "n_gpus": world, "steps": args.steps,
