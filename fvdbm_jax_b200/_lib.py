@@ -23,12 +23,13 @@ VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA, VARIANT_PAIR = 0, 1, 2, 3
 (CELL_PDF, CELL_RHO, CELL_VEL, CELL_PDF_EQ, FACE_FLUX, NODE_PDF, NODE_RHO, NODE_VEL,
  CELL_PDF_PREV) = range(9)
 (INFO_MODE, INFO_STEPS, INFO_LAUNCHES, INFO_TRACKED_NODES, INFO_BOUNDARY_SIDES, INFO_DEVICE_BYTES,
- INFO_VARIANT, INFO_NPAD, INFO_FUSED_OK, INFO_HALO_CELLS, INFO_OWNED_CELLS) = range(11)
+ INFO_VARIANT, INFO_NPAD, INFO_FUSED_OK, INFO_HALO_CELLS, INFO_OWNED_CELLS, INFO_GRAPH_STEPS) = range(12)
 (OPT_VARIANT, OPT_TILE_CELLS, OPT_STAGES, OPT_GRAPH_STEPS, OPT_CTAS_PER_SM, OPT_REVERSE_SWEEP,
  OPT_TEMPORAL, OPT_PREFETCH_DIST) = range(8)
 
 EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_error", "fvdbm_step",
-           "fvdbm_step_timed", "fvdbm_sync", "fvdbm_get", "fvdbm_set", "fvdbm_set_params",
+           "fvdbm_step_timed", "fvdbm_sync", "fvdbm_get", "fvdbm_set", "fvdbm_set_async", "fvdbm_get_async", "fvdbm_wait",
+           "fvdbm_set_params",
            "fvdbm_set_option", "fvdbm_info", "fvdbm_check_finite", "fvdbm_halo_set_lists", "fvdbm_halo_pack",
            "fvdbm_halo_unpack", "fvdbm_step_phase", "fvdbm_stream", "fvdbm_comm_unique_id", "fvdbm_comm_init",
            "fvdbm_halo_set_peers", "fvdbm_plan_create",
@@ -79,6 +80,9 @@ def load():
     lib.fvdbm_sync.argtypes = [H]
     lib.fvdbm_get.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     lib.fvdbm_set.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
+    lib.fvdbm_set_async.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
+    lib.fvdbm_get_async.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
+    lib.fvdbm_wait.argtypes = [H, C.c_int64]
     lib.fvdbm_set_params.argtypes = [H, C.c_double, C.c_double]
     lib.fvdbm_set_option.argtypes = [H, C.c_int, C.c_int64]
     lib.fvdbm_info.argtypes = [H, C.c_int, C.POINTER(C.c_int64)]
@@ -103,6 +107,7 @@ def load():
     lib.fvdbm_plan_scalar.argtypes = [P, C.c_char_p]
     lib.fvdbm_plan_scalar.restype = C.c_int64
     for name in ("fvdbm_step", "fvdbm_step_timed", "fvdbm_step_phase", "fvdbm_sync", "fvdbm_get", "fvdbm_set",
+                 "fvdbm_set_async", "fvdbm_get_async", "fvdbm_wait",
                  "fvdbm_set_params", "fvdbm_set_option", "fvdbm_info", "fvdbm_halo_set_lists",
                  "fvdbm_halo_pack", "fvdbm_halo_unpack", "fvdbm_plan_create"):
         getattr(lib, name).restype = C.c_int

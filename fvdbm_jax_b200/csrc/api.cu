@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <initializer_list>
 
 #include <dlfcn.h>
 #if __has_include(<nccl.h>)
@@ -69,6 +70,9 @@ struct Engine {
     virtual int sync() = 0;
     virtual int get(int field, void* dst, size_t bytes) = 0;
     virtual int set(int field, const void* src, size_t bytes) = 0;
+    virtual int set_async(int field, const void* src, size_t bytes) = 0;
+    virtual int get_async(int field, void* dst, size_t bytes, int64_t* ticket) = 0;
+    virtual int wait_ticket(int64_t ticket) = 0;
     virtual int set_params(double tau, double dt) = 0;
     virtual int set_option(int opt, int64_t v) = 0;
     virtual int info(int key, int64_t* v) const = 0;
@@ -144,7 +148,23 @@ struct EngineT final : Engine {
     DevBuf<int32_t> s_cface, s_csign, s_fcell, s_fnode;
     DevBuf<real> s_fdist, s_fn, s_fL;
     DevBuf<real> s_rho, s_ux, s_uy, s_feq, s_flux;     // staged dynamics (lazy)
-    DevBuf<real> scratch;                              // export/import staging
+    // host <-> device staging in reference layout.  Uploads land in `inbox` on their own copy stream, so the
+    // PCIe transfer overlaps whatever the main stream is still computing; the import kernel is ordered behind
+    // it on the main stream.  Downloads: an export kernel on the main stream fills one of two `outbox` slots,
+    // the D2H copy runs on a second copy stream (full-duplex PCIe, overlaps the next iterations).
+    DevBuf<real> inbox;
+    cudaStream_t xin = nullptr, xout = nullptr;
+    cudaEvent_t inbox_filled = nullptr, inbox_consumed = nullptr;
+    bool inbox_used = false;
+    struct Outbox {
+        DevBuf<real> buf;
+        cudaEvent_t ready = nullptr, drained = nullptr;
+        bool used = false;
+        int64_t moments_steps = -1, moments_rows = 0;   // slot holds [rho | vel] of the populations before step `moments_steps`
+    } outbox[2];
+    static constexpr int kTickets = 32;
+    cudaEvent_t ticket_ev[kTickets] = {};
+    int64_t tickets = 0;
     DevBuf<int32_t> halo_send, halo_recv;
     DevBuf<unsigned long long> counter;
     // native exchange (optional)
@@ -159,6 +179,11 @@ struct EngineT final : Engine {
         cudaSetDevice(device);
         drop_graphs();
         if (comm && g_nccl.CommDestroy) { cudaStreamSynchronize(stream); g_nccl.CommDestroy(comm); }
+        if (xin) { cudaStreamSynchronize(xin); cudaStreamDestroy(xin); }
+        if (xout) { cudaStreamSynchronize(xout); cudaStreamDestroy(xout); }
+        cudaEvent_t evs[] = {inbox_filled, inbox_consumed, outbox[0].ready, outbox[0].drained, outbox[1].ready, outbox[1].drained};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : ticket_ev) if (e) cudaEventDestroy(e);
         if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
         if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -195,6 +220,11 @@ struct EngineT final : Engine {
         CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CU_TRY(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
         CU_TRY(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
+        CU_TRY(cudaStreamCreateWithFlags(&xin, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&xout, cudaStreamNonBlocking));
+        cudaEvent_t* evs[] = {&inbox_filled, &inbox_consumed, &outbox[0].ready, &outbox[0].drained, &outbox[1].ready, &outbox[1].drained};
+        for (cudaEvent_t* e : evs) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t& e : ticket_ev) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         if (const char* e = getenv("FVDBM_OVERLAP")) overlap = atoi(e);
@@ -554,19 +584,44 @@ struct EngineT final : Engine {
 
     int sync() override {
         CU_TRY(cudaSetDevice(device));
+        CU_TRY(cudaStreamSynchronize(xin));
         CU_TRY(cudaStreamSynchronize(stream));
+        CU_TRY(cudaStreamSynchronize(xout));
         CU_TRY(cudaGetLastError());
         return FVDBM_OK;
     }
 
     // ---------------------------------------------------------------- transfers
-    int need_scratch(size_t elems) {
-        if (scratch.n >= elems) return FVDBM_OK;
-        CU_TRY(scratch.alloc(elems));
+    int wait_ticket(int64_t t) override {
+        CU_TRY(cudaSetDevice(device));
+        if (t < 0 || t >= tickets) { err = "unknown transfer ticket"; return FVDBM_ERR_ARG; }
+        if (t + kTickets <= tickets) return FVDBM_OK;            // recycled: that transfer completed long ago
+        CU_TRY(cudaEventSynchronize(ticket_ev[t % kTickets]));
+        return FVDBM_OK;
+    }
+    // D2H of `bytes` from an outbox slot on the download stream; the ticket completes when dst is filled
+    int ship(Outbox& o, const real* src, void* dst, size_t bytes, int64_t* ticket) {
+        CU_TRY(cudaEventRecord(o.ready, stream));
+        CU_TRY(cudaStreamWaitEvent(xout, o.ready, 0));
+        CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, xout));
+        CU_TRY(cudaEventRecord(o.drained, xout));
+        o.used = true;
+        const int64_t t = tickets++;
+        CU_TRY(cudaEventRecord(ticket_ev[t % kTickets], xout));
+        if (ticket) *ticket = t;
+        return FVDBM_OK;
+    }
+    int claim_outbox(Outbox& o, size_t elems) {                 // next export may overwrite the slot once its last D2H drained
+        if (o.buf.n < elems) {
+            if (o.used) CU_TRY(cudaEventSynchronize(o.drained));
+            CU_TRY(o.buf.alloc(elems));
+            o.moments_steps = -1;
+        }
+        if (o.used) CU_TRY(cudaStreamWaitEvent(stream, o.drained, 0));
         return FVDBM_OK;
     }
 
-    int get(int field, void* dst, size_t bytes) override {
+    int get_async(int field, void* dst, size_t bytes, int64_t* ticket) override {
         CU_TRY(cudaSetDevice(device));
         if (!dst) { err = "dst is null"; return FVDBM_ERR_ARG; }
         const int64_t N = plan.N, F = plan.F, Pn = plan.P;
@@ -584,25 +639,36 @@ struct EngineT final : Engine {
         };
         int rc;
         switch (field) {
-        case FVDBM_CELL_PDF: case FVDBM_CELL_PDF_PREV: {
+        case FVDBM_CELL_PDF: case FVDBM_CELL_PDF_PREV: case FVDBM_CELL_PDF_EQ: {
             if (!expect_cells(Q)) return FVDBM_ERR_ARG;
-            if (field == FVDBM_CELL_PDF_PREV && steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
-            if ((rc = need_scratch((size_t)N * Q))) return rc;
-            const real* src = pdf[field == FVDBM_CELL_PDF ? cur : prev].p;
-            k_export_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(src, pos.p, rows, scratch.p);
+            if (field != FVDBM_CELL_PDF && steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
+            Outbox& o = outbox[tickets & 1];
+            if ((rc = claim_outbox(o, (size_t)N * Q))) return rc;
+            o.moments_steps = -1;
+            if (field == FVDBM_CELL_PDF_EQ)
+                k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(P, pdf[prev].p, pos.p, rows, nullptr, nullptr, o.buf.p);
+            else
+                k_export_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[field == FVDBM_CELL_PDF ? cur : prev].p, pos.p, rows, o.buf.p);
             ++launches;
-            break;
+            CU_TRY(cudaGetLastError());
+            return ship(o, o.buf.p, dst, bytes, ticket);
         }
-        case FVDBM_CELL_RHO: case FVDBM_CELL_VEL: case FVDBM_CELL_PDF_EQ: {
-            const size_t per = field == FVDBM_CELL_RHO ? 1 : field == FVDBM_CELL_VEL ? 2 : Q;
-            if (!expect_cells(per)) return FVDBM_ERR_ARG;
+        case FVDBM_CELL_RHO: case FVDBM_CELL_VEL: {
+            // rho and vel share ONE export pass: the slot keeps [rho (rows) | vel (2 rows)] of the lagged
+            // populations, so fetching the second of the two costs no kernel
+            if (!expect_cells(field == FVDBM_CELL_RHO ? 1 : 2)) return FVDBM_ERR_ARG;
             if (steps == 0) { err = "no step taken yet"; return FVDBM_ERR_STATE; }
-            if ((rc = need_scratch((size_t)N * per))) return rc;
-            k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(
-                P, pdf[prev].p, pos.p, rows, field == FVDBM_CELL_RHO ? scratch.p : nullptr,
-                field == FVDBM_CELL_VEL ? scratch.p : nullptr, field == FVDBM_CELL_PDF_EQ ? scratch.p : nullptr);
-            ++launches;
-            break;
+            Outbox* o = nullptr;
+            for (Outbox& c : outbox) if (c.moments_steps == steps && c.moments_rows == rows) o = &c;
+            if (!o) {
+                o = &outbox[tickets & 1];
+                if ((rc = claim_outbox(*o, (size_t)N * 3))) return rc;
+                k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(P, pdf[prev].p, pos.p, rows, o->buf.p, o->buf.p + rows, nullptr);
+                ++launches;
+                CU_TRY(cudaGetLastError());
+                o->moments_steps = steps; o->moments_rows = rows;
+            }
+            return ship(*o, field == FVDBM_CELL_RHO ? o->buf.p : o->buf.p + rows, dst, bytes, ticket);
         }
         case FVDBM_FACE_FLUX: {
             if (!expect((size_t)F * Q)) return FVDBM_ERR_ARG;
@@ -611,7 +677,7 @@ struct EngineT final : Engine {
             if (mode != FVDBM_MODE_STAGED && (rc = launch_faces(pdf[prev].p))) return rc;
             CU_TRY(cudaMemcpyAsync(dst, s_flux.p, bytes, cudaMemcpyDeviceToHost, stream));
             CU_TRY(cudaStreamSynchronize(stream));
-            return FVDBM_OK;
+            break;
         }
         case FVDBM_NODE_PDF: case FVDBM_NODE_RHO: case FVDBM_NODE_VEL: {
             const size_t per = field == FVDBM_NODE_RHO ? 1 : field == FVDBM_NODE_VEL ? 2 : Q;
@@ -623,32 +689,46 @@ struct EngineT final : Engine {
             real* out = static_cast<real*>(dst);
             for (int64_t t = 0; t < plan.NT; ++t)
                 for (size_t j = 0; j < per; ++j) out[(size_t)plan.tn_orig[t] * per + j] = host[j * plan.NTpad + t];
-            return FVDBM_OK;
+            break;
         }
         default: err = "unknown field"; return FVDBM_ERR_ARG;
         }
-        CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync(dst, scratch.p, bytes, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(cudaStreamSynchronize(stream));
+        // fields served synchronously (O(sqrt N) node data, the staged flux observable): already complete
+        const int64_t t = tickets++;
+        CU_TRY(cudaEventRecord(ticket_ev[t % kTickets], stream));
+        if (ticket) *ticket = t;
         return FVDBM_OK;
     }
 
-    int set(int field, const void* src, size_t bytes) override {
+    int get(int field, void* dst, size_t bytes) override {
+        int64_t t = -1;
+        int rc = get_async(field, dst, bytes, &t);
+        return rc ? rc : wait_ticket(t);
+    }
+
+    // upload; returns once `src` may be reused when wait_host is set, immediately otherwise (src must then stay
+    // valid until fvdbm_sync / a later blocking call).  The state change itself is ordered on the main stream.
+    int set_impl(int field, const void* src, size_t bytes, bool wait_host) {
         CU_TRY(cudaSetDevice(device));
         if (!src) { err = "src is null"; return FVDBM_ERR_ARG; }
         const int64_t N = plan.N, Pn = plan.P;
-        int rc;
         switch (field) {
         case FVDBM_CELL_PDF: {
             int64_t rows = N;                 // all local cells, or only the owned prefix
             if (bytes == (size_t)plan.No * Q * sizeof(real)) rows = plan.No;
             else if (bytes != (size_t)N * Q * sizeof(real)) { err = "size mismatch for field"; return FVDBM_ERR_ARG; }
-            if ((rc = need_scratch((size_t)N * Q))) return rc;
-            CU_TRY(cudaMemcpyAsync(scratch.p, src, bytes, cudaMemcpyHostToDevice, stream));
-            k_import_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[cur].p, pos.p, rows, scratch.p);
+            if (inbox.n < (size_t)N * Q) CU_TRY(inbox.alloc((size_t)N * Q));
+            if (inbox_used) CU_TRY(cudaStreamWaitEvent(xin, inbox_consumed, 0));     // previous import has read the inbox
+            CU_TRY(cudaMemcpyAsync(inbox.p, src, bytes, cudaMemcpyHostToDevice, xin));
+            CU_TRY(cudaEventRecord(inbox_filled, xin));
+            CU_TRY(cudaStreamWaitEvent(stream, inbox_filled, 0));
+            k_import_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[cur].p, pos.p, rows, inbox.p);
             ++launches;
             CU_TRY(cudaGetLastError());
-            CU_TRY(cudaStreamSynchronize(stream));
+            CU_TRY(cudaEventRecord(inbox_consumed, stream));
+            inbox_used = true;
+            for (Outbox& o : outbox) o.moments_steps = -1;
+            if (wait_host) CU_TRY(cudaEventSynchronize(inbox_filled));
             return FVDBM_OK;
         }
         case FVDBM_NODE_PDF: case FVDBM_NODE_RHO: case FVDBM_NODE_VEL: {
@@ -666,6 +746,8 @@ struct EngineT final : Engine {
         default: err = "field is not settable"; return FVDBM_ERR_ARG;
         }
     }
+    int set(int field, const void* src, size_t bytes) override { return set_impl(field, src, bytes, true); }
+    int set_async(int field, const void* src, size_t bytes) override { return set_impl(field, src, bytes, false); }
 
     int check_finite(int64_t* bad) override {
         CU_TRY(cudaSetDevice(device));
@@ -725,7 +807,7 @@ struct EngineT final : Engine {
                            bf_ratio.bytes() + pos.bytes() + ipos.bytes() + ring_cell.bytes() + ring_w.bytes() + tn_type.bytes() +
                            npdf.bytes() + nrho.bytes() + nvel.bytes() + s_cface.bytes() + s_csign.bytes() + s_fcell.bytes() +
                            s_fnode.bytes() + s_fdist.bytes() + s_fn.bytes() + s_fL.bytes() + s_inv_area.bytes() + s_rho.bytes() +
-                           s_ux.bytes() + s_uy.bytes() + s_feq.bytes() + s_flux.bytes() + scratch.bytes() + halo_send.bytes() +
+                           s_ux.bytes() + s_uy.bytes() + s_feq.bytes() + s_flux.bytes() + inbox.bytes() + outbox[0].buf.bytes() + outbox[1].buf.bytes() + halo_send.bytes() +
                            halo_recv.bytes() + sendbuf.bytes() + recvbuf.bytes() + counter.bytes());
             break;
         case FVDBM_INFO_VARIANT: *v = variant; break;
@@ -733,6 +815,7 @@ struct EngineT final : Engine {
         case FVDBM_INFO_FUSED_OK: *v = plan.fused_ok ? 1 : 0; break;
         case FVDBM_INFO_HALO_CELLS: *v = plan.N - plan.No; break;
         case FVDBM_INFO_OWNED_CELLS: *v = plan.No; break;
+        case FVDBM_INFO_GRAPH_STEPS: *v = graph_steps; break;
         default: return FVDBM_ERR_ARG;
         }
         return FVDBM_OK;
@@ -860,6 +943,9 @@ int fvdbm_step_phase(fvdbm_handle* h, int phase) { return h ? h->e->step_phase(p
 int fvdbm_sync(fvdbm_handle* h) { return h ? h->e->sync() : FVDBM_ERR_ARG; }
 int fvdbm_get(fvdbm_handle* h, int field, void* dst, size_t bytes) { return h ? h->e->get(field, dst, bytes) : FVDBM_ERR_ARG; }
 int fvdbm_set(fvdbm_handle* h, int field, const void* src, size_t bytes) { return h ? h->e->set(field, src, bytes) : FVDBM_ERR_ARG; }
+int fvdbm_set_async(fvdbm_handle* h, int field, const void* src, size_t bytes) { return h ? h->e->set_async(field, src, bytes) : FVDBM_ERR_ARG; }
+int fvdbm_get_async(fvdbm_handle* h, int field, void* dst, size_t bytes, int64_t* ticket) { return h ? h->e->get_async(field, dst, bytes, ticket) : FVDBM_ERR_ARG; }
+int fvdbm_wait(fvdbm_handle* h, int64_t ticket) { return h ? h->e->wait_ticket(ticket) : FVDBM_ERR_ARG; }
 int fvdbm_set_params(fvdbm_handle* h, double tau, double dt) { return h ? h->e->set_params(tau, dt) : FVDBM_ERR_ARG; }
 int fvdbm_set_option(fvdbm_handle* h, int opt, int64_t v) { return h ? h->e->set_option(opt, v) : FVDBM_ERR_ARG; }
 int fvdbm_info(const fvdbm_handle* h, int key, int64_t* v) { return h ? h->e->info(key, v) : FVDBM_ERR_ARG; }

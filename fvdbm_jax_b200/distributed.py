@@ -285,12 +285,16 @@ class DistributedEnvironment:
         self.env.sync()
         return self
 
-    def get_into(self, name, out):
+    def get_into(self, name, out, wait=True):
         """Owned rows of a local cell field straight into ``out`` ((n_owned, width), e.g. pinned)."""
-        return self.env.get_into(name, out)
+        return self.env.get_into(name, out, wait=wait)
 
-    def set_cells_pdf(self, owned_pdf: np.ndarray):
-        self.env.set_cells_pdf(owned_pdf)
+    def set_cells_pdf(self, owned_pdf: np.ndarray, wait=True):
+        self.env.set_cells_pdf(owned_pdf, wait=wait)
+        return self
+
+    def wait(self, ticket=None):
+        self.env.wait(ticket)
         return self
 
     def close(self):

@@ -7,7 +7,11 @@ enqueues hand-written sm_100a kernels through the C ABI of libfvdbm_b200.so inst
 jit.  Differences a caller can observe:
 
 * ``step(n=1)``: optional step count (one C call, CUDA-graph batched); still returns an env
-  (``self``), so ``env = env.step()`` keeps working.
+  (``self``), so ``env = env.step()`` keeps working.  The literal notebook loop
+  ``for i in range(100000): env = env.step()`` (tests/flow_over_cyl.ipynb c17) is batched too: single
+  steps only bump a pending counter that is flushed -- through the same CUDA-graph path as ``step(n)`` --
+  every ``defer_batch`` steps and before anything observes or changes the state (any attribute read,
+  ``sync``, assignment, pickling).  ``Environment.defer = False`` restores one C call per ``step()``.
 * dynamic arrays are host NumPy arrays materialised on demand, in the ORIGINAL element numbering
   and the reference's shapes, with the reference's one-step lag for rho / vel / pdf_eq / flux
   (SURVEY.md A.2).
@@ -97,6 +101,7 @@ class Environment:
     device = 0
     reorder = "auto"            # 'auto' | 'hilbert' | 'rcm' | 'none' | explicit permutation
     mode = "auto"               # 'auto' | 'fused' | 'staged'
+    defer = True                # batch single step() calls (see module docstring)
 
     def __init__(self, cells, faces, nodes, dtype=None, device=None, reorder=None, mode=None,
                  n_owned=0):
@@ -129,7 +134,10 @@ class Environment:
     def _attach(self, cells, faces, nodes):
         self._handle = None
         self._lib = None
+        self._closed = False
         self._steps = 0
+        self._pending = 0
+        self._batch = 32
         self._cache = {}
         self._host = {}
         self._options = {}
@@ -195,6 +203,8 @@ class Environment:
         """Create the device engine (done implicitly by the first ``step``)."""
         if self._handle is not None:
             return self
+        if self._closed:
+            raise RuntimeError("this Environment was closed; its device state is gone (pickle it before close() to keep it)")
         lib = _lib.load()                      # raises if the CUDA library is not built
         da = self._describe()
         h = C.c_void_p()
@@ -205,20 +215,38 @@ class Environment:
                        "nodes.rho": (da.P, 1), "nodes.vel": (da.P, 2)}
         for k, v in self._options.items():
             _lib.check(lib.fvdbm_set_option(h, k, v), h)
+        self._set_batch()
         return self
+
+    def _set_batch(self):
+        g = C.c_int64()
+        _lib.check(self._lib.fvdbm_info(self._handle, _lib.INFO_GRAPH_STEPS, C.byref(g)), self._handle)
+        self._batch = int(g.value) if g.value > 0 else 32      # one CUDA-graph launch (or 32 plain iterations) per flush
+
+    def _flush(self):
+        """Hand the deferred single steps to the engine (one C call)."""
+        if self._pending:
+            n, self._pending = self._pending, 0
+            _lib.check(self._lib.fvdbm_step(self._handle, n), self._handle)
 
     def step(self, n: int = 1):
         """n iterations of reference ``Environment.step`` (environment.py:55-65); asynchronous."""
         self.build()
-        _lib.check(self._lib.fvdbm_step(self._handle, int(n)), self._handle)
+        n = int(n)
+        if n < 0:
+            raise ValueError("nsteps must be >= 0")
         if n > 0:
-            self._steps += int(n)
+            self._pending += n
+            self._steps += n
             self._cache.clear()
+            if n != 1 or not self.defer or self._pending >= self._batch:
+                self._flush()
         return self
 
     def step_timed(self, n: int) -> float:
         """Like ``step(n)`` but blocks and returns the device time in milliseconds (CUDA events)."""
         self.build()
+        self._flush()
         ms = C.c_float()
         _lib.check(self._lib.fvdbm_step_timed(self._handle, int(n), C.byref(ms)), self._handle)
         if n > 0:
@@ -228,17 +256,29 @@ class Environment:
 
     def sync(self):
         if self._handle is not None:
+            self._flush()
             _lib.check(self._lib.fvdbm_sync(self._handle), self._handle)
+        return self
+
+    def wait(self, ticket=None):
+        """Block until the transfer with this ticket (from ``get_into(..., wait=False)``) has filled its host
+        array; ``None`` waits for everything enqueued (= ``sync``)."""
+        if ticket is None:
+            return self.sync()
+        _lib.check(self._lib.fvdbm_wait(self._handle, int(ticket)), self._handle)
         return self
 
     def set_option(self, option: int, value: int):
         self._options[option] = int(value)
         if self._handle is not None:
+            self._flush()
             _lib.check(self._lib.fvdbm_set_option(self._handle, option, int(value)), self._handle)
+            self._set_batch()
         return self
 
     def set_params(self, tau: float, delta_t: float):
         self.build()
+        self._flush()
         _lib.check(self._lib.fvdbm_set_params(self._handle, float(tau), float(delta_t)), self._handle)
         return self
 
@@ -246,12 +286,14 @@ class Environment:
         """Number of cells whose populations hold a NaN/Inf (the reference has no such check: a
         diverged run is only visible in the plots)."""
         self.build()
+        self._flush()
         v = C.c_int64()
         _lib.check(self._lib.fvdbm_check_finite(self._handle, C.byref(v)), self._handle)
         return int(v.value)
 
     def info(self, key: int) -> int:
         self.build()
+        self._flush()
         v = C.c_int64()
         _lib.check(self._lib.fvdbm_info(self._handle, key, C.byref(v)), self._handle)
         return int(v.value)
@@ -266,6 +308,7 @@ class Environment:
         lagged = name in ("cells.rho", "cells.vel", "cells.pdf_eq", "faces.pdf")
         if lagged and self._steps == 0:
             return self._host[name]
+        self._flush()
         shape = self._shape[name]
         if name.startswith("nodes."):
             out = np.array(self._host[name], copy=True)          # untracked rows keep their values
@@ -277,35 +320,46 @@ class Environment:
         self._cache[name] = out
         return out
 
-    def get_into(self, name: str, out: np.ndarray):
-        """Download field ``name`` ("cells.rho", ...) into a caller-owned (e.g. pinned) array."""
+    def get_into(self, name: str, out: np.ndarray, wait: bool = True):
+        """Download field ``name`` ("cells.rho", ...) into a caller-owned (e.g. pinned) array.  With
+        ``wait=False`` the export + D2H copy are only enqueued (they overlap later iterations) and a ticket
+        for ``wait(ticket)`` is returned instead of the array."""
         self.build()
+        self._flush()
         full = int(np.prod(self._shape[name]))
         owned = self._n_owned * self._shape[name][1] if (self._n_owned and name.startswith("cells.")) else full
         if out.dtype != self.real or out.size not in (full, owned) or not out.flags.c_contiguous:
             raise ValueError("out must be a contiguous array of the engine dtype holding all (or all owned) rows")
-        _lib.check(self._lib.fvdbm_get(self._handle, _FIELD[name], out.ctypes.data, out.nbytes), self._handle)
-        return out
+        if wait:
+            _lib.check(self._lib.fvdbm_get(self._handle, _FIELD[name], out.ctypes.data, out.nbytes), self._handle)
+            return out
+        t = C.c_int64()
+        _lib.check(self._lib.fvdbm_get_async(self._handle, _FIELD[name], out.ctypes.data, out.nbytes, C.byref(t)), self._handle)
+        return int(t.value)
 
     # ------------------------------------------------------------------ multi-GPU primitives
     def halo_set_lists(self, send_cells: np.ndarray, recv_cells: np.ndarray):
         """Local ids (original local numbering) of the cells packed for / unpacked from peers."""
         self.build()
+        self._flush()
         s = np.ascontiguousarray(send_cells, dtype=np.int32)
         r = np.ascontiguousarray(recv_cells, dtype=np.int32)
         _lib.check(self._lib.fvdbm_halo_set_lists(self._handle, s.ctypes.data, s.size, r.ctypes.data, r.size), self._handle)
         return self
 
     def halo_pack(self, dev_ptr: int):
+        self._flush()
         _lib.check(self._lib.fvdbm_halo_pack(self._handle, C.c_void_p(dev_ptr)), self._handle)
 
     def halo_unpack(self, dev_ptr: int):
+        self._flush()
         _lib.check(self._lib.fvdbm_halo_unpack(self._handle, C.c_void_p(dev_ptr)), self._handle)
 
     def comm_attach(self, nranks: int, rank: int, unique_id: bytes, peers_send, send_counts, peers_recv, recv_counts):
         """Native exchange: give the engine its own NCCL communicator and the per-peer layout of the
         halo lists; afterwards ``step(n)`` runs complete distributed iterations inside the library."""
         self.build()
+        self._flush()
         buf = C.create_string_buffer(bytes(unique_id), _lib.COMM_ID_BYTES)
         _lib.check(self._lib.fvdbm_comm_init(self._handle, int(nranks), int(rank), buf), self._handle)
         sp = np.ascontiguousarray(peers_send, dtype=np.int32); sc = np.ascontiguousarray(send_counts, dtype=np.int64)
@@ -318,6 +372,7 @@ class Environment:
         """phase 0: interior cells (no halo / boundary dependence); phase 1: node kernel + border
         cells + buffer swap (completes the step)."""
         self.build()
+        self._flush()
         _lib.check(self._lib.fvdbm_step_phase(self._handle, int(phase)), self._handle)
         if phase == 1:
             self._steps += 1
@@ -329,14 +384,18 @@ class Environment:
         self.build()
         return int(self._lib.fvdbm_stream(self._handle) or 0)
 
-    def set_cells_pdf(self, arr: np.ndarray):
-        """Upload populations from a caller-owned (e.g. pinned) (N,Q) array of the engine dtype."""
+    def set_cells_pdf(self, arr: np.ndarray, wait: bool = True):
+        """Upload populations from a caller-owned (e.g. pinned) (N,Q) array of the engine dtype.  With
+        ``wait=False`` the copy is only enqueued on the engine's upload stream (it overlaps the iterations
+        already enqueued); ``arr`` must then stay untouched until ``sync()`` / a later ``wait``."""
         self.build()
+        self._flush()
         full = int(np.prod(self._shape["cells.pdf"]))
         owned = self._n_owned * self._shape["cells.pdf"][1] if self._n_owned else full
         if arr.dtype != self.real or arr.size not in (full, owned) or not arr.flags.c_contiguous:
             raise ValueError("arr must be a contiguous (N,Q) or (N_owned,Q) array of the engine dtype")
-        _lib.check(self._lib.fvdbm_set(self._handle, _lib.CELL_PDF, arr.ctypes.data, arr.nbytes), self._handle)
+        fn = self._lib.fvdbm_set if wait else self._lib.fvdbm_set_async
+        _lib.check(fn(self._handle, _lib.CELL_PDF, arr.ctypes.data, arr.nbytes), self._handle)
         self._cache.pop("cells.pdf", None)
         return self
 
@@ -347,6 +406,7 @@ class Environment:
             return
         if name not in _SETTABLE:
             raise AttributeError(f"{name} is derived state (recomputed every step) and cannot be assigned")
+        self._flush()
         arr = np.ascontiguousarray(_np(value), dtype=self.real).reshape(self._shape[name])
         _lib.check(self._lib.fvdbm_set(self._handle, _FIELD[name], arr.ctypes.data, arr.nbytes), self._handle)
         if name.startswith("nodes."):
@@ -358,6 +418,7 @@ class Environment:
         if getattr(self, "_handle", None) is not None:
             self._lib.fvdbm_destroy(self._handle)
             self._handle = None
+            self._closed = True          # a later step()/fetch raises instead of silently restarting from t = 0
 
     def __del__(self):
         try:

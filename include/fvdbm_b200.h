@@ -22,7 +22,8 @@
  * `real` is float when dtype==32 and double when dtype==64.
  *
  * Threading: one handle = one device + one CUDA stream; calls on a handle are not thread-safe,
- * distinct handles are independent.  fvdbm_step only enqueues work; fvdbm_get / fvdbm_sync block.
+ * distinct handles are independent.  fvdbm_step only enqueues work; fvdbm_get / fvdbm_sync block;
+ * fvdbm_set returns when the source buffer may be reused (the import is stream-ordered).
  * Errors: every int-returning call gives 0 on success, <0 on failure; fvdbm_last_error(h) (or
  * fvdbm_last_error(NULL) for create-time failures) returns the message.
  */
@@ -91,7 +92,8 @@ enum fvdbm_info_key {
     FVDBM_INFO_NPAD = 7,
     FVDBM_INFO_FUSED_OK = 8,      /* 1 if the mesh admits the fused path                   */
     FVDBM_INFO_HALO_CELLS = 9,
-    FVDBM_INFO_OWNED_CELLS = 10
+    FVDBM_INFO_OWNED_CELLS = 10,
+    FVDBM_INFO_GRAPH_STEPS = 11   /* iterations per CUDA-graph launch (0 = graphs off): the natural batch size */
 };
 
 enum fvdbm_option {
@@ -161,6 +163,15 @@ int  fvdbm_sync(fvdbm_handle* h);
 /* host <-> device transfer of one field in reference layout; bytes must match exactly */
 int  fvdbm_get(fvdbm_handle* h, int field, void* dst, size_t bytes);
 int  fvdbm_set(fvdbm_handle* h, int field, const void* src, size_t bytes);
+/* Pipelined variants for callers that stream data every few iterations (e.g. coupling, in-situ output).
+ * fvdbm_set_async: the H2D copy runs on its own stream and overlaps the iterations already enqueued; the state
+ *   change is ordered behind them.  `src` must stay valid until fvdbm_sync (or any later fvdbm_wait / fvdbm_get).
+ * fvdbm_get_async: an export pass ordered behind the enqueued iterations fills a device staging slot (two
+ *   slots; cells.rho and cells.vel share one pass), the D2H copy then overlaps later iterations.  `dst` is
+ *   complete once fvdbm_wait(h, *ticket) returns.  Use pinned host memory for real overlap. */
+int  fvdbm_set_async(fvdbm_handle* h, int field, const void* src, size_t bytes);
+int  fvdbm_get_async(fvdbm_handle* h, int field, void* dst, size_t bytes, int64_t* ticket);
+int  fvdbm_wait(fvdbm_handle* h, int64_t ticket);
 /* change tau / delta_t without rebuilding (they are Python floats baked into the jit in the
    reference, src/dynamics.py:65-68) */
 int  fvdbm_set_params(fvdbm_handle* h, double tau, double delta_t);

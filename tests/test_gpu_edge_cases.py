@@ -142,3 +142,63 @@ def test_divergence_is_detected():
     bad = env.count_nonfinite()
     assert bad > 0 and bad == int(np.count_nonzero(~np.isfinite(env.cells.pdf).all(axis=1)))
     env.close()
+
+
+def test_literal_notebook_loop_is_deferred_and_equal_to_step_n():
+    """`for i in range(n): env = env.step()` (tests/flow_over_cyl.ipynb c17) is batched behind the scenes and
+    must give the bits of step(n); anything that observes the state flushes first (lag semantics intact)."""
+    case = golden.Case("channel_lw")
+    a = fb.Environment(*case.containers(), dtype=np.float32)
+    a.init()
+    a = a.step(137)
+    b = fb.Environment(*case.containers(), dtype=np.float32)
+    b.init()
+    for i in range(137):
+        b = b.step()
+        if i == 4:                                   # observed mid-loop: golden state after 5 steps, lagged moments
+            for name in golden.STATE:
+                obj, attr = name.split(".")
+                assert golden.rel_err(getattr(getattr(b, obj), attr), case.expected(5, name)) < 1e-5, name
+    assert b._pending > 0                            # single steps are really being deferred ...
+    launches_before = b._pending
+    np.testing.assert_array_equal(b.cells.pdf, a.cells.pdf)      # ... and flushed by the read
+    assert b._pending == 0 and launches_before < b._batch
+    np.testing.assert_array_equal(b.cells.rho, a.cells.rho)
+    np.testing.assert_array_equal(b.nodes.pdf, a.nodes.pdf)
+    assert b.info(_lib.INFO_STEPS) == 137
+    a.close(); b.close()
+    with pytest.raises(RuntimeError, match="closed"):
+        b.step()
+
+
+def test_async_transfers_match_blocking_ones():
+    import torch
+    case = golden.Case("cylinder_lw")
+    env = fb.Environment(*case.containers(), dtype=np.float32)
+    env.init()
+    env = env.step(3)
+    n = case.static["cells.face_indices"].shape[0]
+    pdf = torch.empty((n, 9), dtype=torch.float32).pin_memory()
+    env.get_into("cells.pdf", pdf.numpy())
+    ref = fb.Environment(*case.containers(), dtype=np.float32)
+    ref.init()
+    ref.cells.pdf = pdf.numpy().copy()
+    ref = ref.step(7)
+    rho = [torch.empty((n, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
+    vel = [torch.empty((n, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    tickets = []
+    for k in range(4):                               # pipelined: upload k+1 / download k-1 overlap step k
+        env.set_cells_pdf(pdf.numpy(), wait=False)
+        env.step(7)
+        env.get_into("cells.rho", rho[k & 1].numpy(), wait=False)
+        tickets.append(env.get_into("cells.vel", vel[k & 1].numpy(), wait=False))
+        if k:
+            env.wait(tickets[k - 1])
+            np.testing.assert_array_equal(rho[(k - 1) & 1].numpy(), ref.cells.rho)
+            np.testing.assert_array_equal(vel[(k - 1) & 1].numpy(), ref.cells.vel)
+    env.wait()
+    np.testing.assert_array_equal(vel[1].numpy(), ref.cells.vel)
+    np.testing.assert_array_equal(env.cells.pdf, ref.cells.pdf)
+    with pytest.raises(ValueError, match="ticket"):
+        env.wait(10 ** 6)
+    env.close(); ref.close()

@@ -49,8 +49,20 @@ def main():
             steps = args.steps if n < 1_000_000 else 400
             best = min(env.step_timed(steps) for _ in range(3))
             t0 = time.perf_counter(); env.step(steps); env.sync(); wall = (time.perf_counter() - t0) * 1e3
+            # the literal notebook loop (tests/flow_over_cyl.ipynb c17): one step() per Python iteration
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                env = env.step()
+            env.sync(); loop = (time.perf_counter() - t0) * 1e3
+            fb.Environment.defer = False
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                env = env.step()
+            env.sync(); loop_nodefer = (time.perf_counter() - t0) * 1e3
+            fb.Environment.defer = True
             print(json.dumps({"config": name, "cells": n, "graph_steps": g, "us_per_step": round(best / steps * 1e3, 2),
                               "wall_us_per_step": round(wall / steps * 1e3, 2),
+                              "loop_us_per_step": round(loop / steps * 1e3, 2), "loop_no_defer_us_per_step": round(loop_nodefer / steps * 1e3, 2),
                               "MCUPS": round(n * steps / best / 1e3, 1), "finite": bool(np.isfinite(env.cells.rho).all())}), flush=True)
         env.close()
 
