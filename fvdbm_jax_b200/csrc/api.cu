@@ -291,7 +291,13 @@ struct EngineT final : Engine {
     }
     size_t max_smem = 0;
     int occ_cache = 0;
-    static constexpr int default_variant() { return sizeof(real) == 4 ? FVDBM_VARIANT_PAIR : FVDBM_VARIANT_DIRECT; }
+    // fp32, >= 4M owned cells (bandwidth-bound regime): the packed two-cells-per-thread kernel -- same speed as the
+    // thread-per-cell kernel at the DRAM limit with half the instructions issued.  Smaller meshes are latency-bound
+    // (node kernel -> border cells chain); there the shorter per-thread critical path of the thread-per-cell kernel
+    // wins by 3-25 % (profiles/r2_small_configs_by_variant.jsonl).  fp64: thread-per-cell.
+    int default_variant() const {
+        return (sizeof(real) == 4 && plan.No >= (int64_t(1) << 22)) ? FVDBM_VARIANT_PAIR : FVDBM_VARIANT_DIRECT;
+    }
 
     size_t stage_bytes(int tc) const { return tma_stage_bytes<real, Q, K, SCHEME>(tc); }
 

@@ -132,14 +132,16 @@ def test_gpu_bits_equal_the_cpu_walk_of_the_same_operation_sequence(name, dtype)
     case = golden.Case(name)
     s = case.steps[-1]
     cpu = test_hostsim.run(case, dtype, s)
-    cells, faces, nodes = case.containers()
-    env = fb.Environment(cells, faces, nodes, dtype=dtype, mode="fused", reorder="none")
-    env.init()
-    env = env.step(s)
-    for key in ("cells.pdf", "cells.rho", "cells.vel", "nodes.pdf", "nodes.rho", "nodes.vel"):
-        obj, attr = key.split(".")
-        np.testing.assert_array_equal(getattr(getattr(env, obj), attr), cpu[key], err_msg=f"{name} {key}")
-    env.close()
+    for variant in ((_lib.VARIANT_PAIR, _lib.VARIANT_DIRECT, _lib.VARIANT_TMA) if dtype is np.float32 else (_lib.VARIANT_DIRECT,)):
+        cells, faces, nodes = case.containers()
+        env = fb.Environment(cells, faces, nodes, dtype=dtype, mode="fused", reorder="none")
+        env.init()
+        env.set_option(_lib.OPT_VARIANT, variant)
+        env = env.step(s)
+        for key in ("cells.pdf", "cells.rho", "cells.vel", "nodes.pdf", "nodes.rho", "nodes.vel"):
+            obj, attr = key.split(".")
+            np.testing.assert_array_equal(getattr(getattr(env, obj), attr), cpu[key], err_msg=f"{name} {key} variant {variant}")
+        env.close()
 
 
 def test_fused_variants_bitwise_identical():
@@ -289,8 +291,8 @@ def test_full_size_properties():
     rho_lag = env.cells.rho.copy()
     prev = np.empty((n, 9), np.float32)
     env.get_into("cells.pdf", prev)                     # current
-    assert env.info(_lib.INFO_VARIANT) == _lib.VARIANT_PAIR            # the default fp32 kernel produced `a`
-    for variant, reverse in ((_lib.VARIANT_TMA, 0), (_lib.VARIANT_DIRECT, 1)):
+    assert env.info(_lib.INFO_VARIANT) == (_lib.VARIANT_PAIR if n >= 1 << 22 else _lib.VARIANT_DIRECT)   # default kernel produced `a`
+    for variant, reverse in ((_lib.VARIANT_TMA, 0), (_lib.VARIANT_DIRECT, 1), (_lib.VARIANT_PAIR, 1)):
         env.set_option(_lib.OPT_VARIANT, variant).set_option(_lib.OPT_REVERSE_SWEEP, reverse)
         assert env.info(_lib.INFO_VARIANT) == variant
         env.cells.pdf = f0

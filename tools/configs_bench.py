@@ -28,6 +28,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--graphs", default="0,10,50")
     ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--variants", default="0", help="comma list of FVDBM_VARIANT_* (0 = the engine's default)")
+    ap.add_argument("--prefetch", default="-1", help="comma list of L2 prefetch distances (-1 = default)")
     args = ap.parse_args()
     def built():
         name, (cells, faces, nodes) = quad_ldc()
@@ -43,8 +45,12 @@ def main():
         n = np.asarray(cells.face_indices).shape[0]
         env = fb.Environment(cells, faces, nodes, dtype=np.float32)
         env.init(); env.build()
-        for g in [int(x) for x in args.graphs.split(",")]:
+        combos = [(int(g), int(v), int(pf)) for g in args.graphs.split(",") for v in args.variants.split(",") for pf in args.prefetch.split(",")]
+        for g, variant, pf in combos:
             env.set_option(_lib.OPT_GRAPH_STEPS, g)
+            env.set_option(_lib.OPT_VARIANT, variant)
+            if pf >= 0:
+                env.set_option(_lib.OPT_PREFETCH_DIST, pf)
             env.step(200); env.sync()
             steps = args.steps if n < 1_000_000 else 400
             best = min(env.step_timed(steps) for _ in range(3))
@@ -60,7 +66,7 @@ def main():
                 env = env.step()
             env.sync(); loop_nodefer = (time.perf_counter() - t0) * 1e3
             fb.Environment.defer = True
-            print(json.dumps({"config": name, "cells": n, "graph_steps": g, "us_per_step": round(best / steps * 1e3, 2),
+            print(json.dumps({"config": name, "cells": n, "graph_steps": g, "variant": env.info(_lib.INFO_VARIANT), "prefetch": pf, "us_per_step": round(best / steps * 1e3, 2),
                               "wall_us_per_step": round(wall / steps * 1e3, 2),
                               "loop_us_per_step": round(loop / steps * 1e3, 2), "loop_no_defer_us_per_step": round(loop_nodefer / steps * 1e3, 2),
                               "MCUPS": round(n * steps / best / 1e3, 1), "finite": bool(np.isfinite(env.cells.rho).all())}), flush=True)
