@@ -125,6 +125,31 @@ def cpu_baseline(scheme, problem, seconds=12.0):
                       "JAX is not installed on the box so the reference's jitted CPU step cannot be timed"}
 
 
+def square_raw_and_callbacks(nx, ny, dyn):
+    """Global raw mesh (points + elements only) of the benchmark square and the BC / initial-state callbacks the
+    window-based decomposition applies per rank -- the same physics as build_problem()."""
+    from fvdbm_jax_b200 import meshgen
+    raw = meshgen.triangulated_square(nx, ny, jitter=0.2, seed=0, periodic_x=True, with_faces=False)
+
+    def bcs(m, nodes):
+        nodes = m.set_vel_node(nodes, meshgen.BOTTOM, np.array([0.0, 0.0]))
+        return m.set_vel_node(nodes, meshgen.TOP, np.array([0.1, 0.0]))
+
+    def init(m):
+        c = m.cell_centers
+        rho = 1 + 0.01 * np.sin(2 * np.pi * c[:, 0] / nx) * np.sin(2 * np.pi * c[:, 1] / ny)
+        u = 0.05 * np.stack([np.sin(2 * np.pi * c[:, 1] / ny), np.sin(2 * np.pi * c[:, 0] / nx)], axis=1)
+        return dyn.calc_eq(rho, u)
+    return raw, bcs, init
+
+
+def porous_raw_and_callbacks(scale, dyn):
+    """BASELINE.json configs[2]: the porous obstacle field (reference outlines), BCs of tests/porous_flow.ipynb."""
+    from fvdbm_jax_b200 import meshgen
+    raw = meshgen.porous_channel(scale=scale)
+    return raw, (lambda m, nodes: meshgen.porous_boundary_conditions(m, nodes)), None
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this process (and therefore its first-touch pinned buffers) to the CPUs of the GPU's NUMA node."""
     try:
@@ -149,14 +174,16 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
-def multi_gpu_check(rank, world, local_dev, scheme, real, nx=40, rows=24, iters=20):
-    """N>1 only, before the timed region: a small strip problem (nx x rows quads per rank) stepped through
-    the SAME native path as the benchmark (engine-owned NCCL send/recv inside fvdbm_step) must equal,
-    bit for bit, the whole mesh stepped by one handle on rank 0."""
+def multi_gpu_check(rank, world, local_dev, scheme, real, nx=40, rows=24, iters=20, partition="strips"):
+    """N>1 only, before the timed region: a small problem (nx x rows quads per rank) stepped through
+    the SAME native path as the benchmark (engine-owned NCCL send/recv inside fvdbm_step, the same kind of
+    partition) must equal, bit for bit, the whole mesh stepped by one handle on rank 0."""
     import torch.distributed as dist
     import fvdbm_jax_b200 as fb
     from fvdbm_jax_b200.distributed import DistributedEnvironment, strip_local_mesh, containers_from_mesh
     dyn = fb.D2Q9(tau=0.8, delta_t=0.1)
+    if partition == "sfc":
+        return multi_gpu_check_sfc(rank, world, local_dev, scheme, real, dyn, nx, rows * world, iters)
     lm, fpc = strip_local_mesh(nx, rows, rank, world, dyn, scheme)
     denv = DistributedEnvironment(lm, dyn, scheme, real, local_dev, 2 * nx * rows * world, fpc, native=True)
     denv.step(iters)
@@ -179,6 +206,36 @@ def multi_gpu_check(rank, world, local_dev, scheme, real, nx=40, rows=24, iters=
         out = {"bitwise_equal": bool(np.array_equal(got, ref)), "ranks": world, "cells": int(ref.shape[0]),
                "iterations": iters, "peers_per_rank": [int(p[2]) for p in parts],
                "what": f"{nx}x{rows}-quad strip per rank, native NCCL path vs one handle on rank 0"}
+    dist.barrier()
+    return out
+
+
+def multi_gpu_check_sfc(rank, world, local_dev, scheme, real, dyn, nx, ny, iters):
+    import torch.distributed as dist
+    import fvdbm_jax_b200 as fb
+    from fvdbm_jax_b200.distributed import DistributedEnvironment
+    raw, bcs, init = square_raw_and_callbacks(nx, ny, dyn)
+    denv = DistributedEnvironment.from_raw(raw, dyn, scheme, real, rank, world, local_dev, bcs, init)
+    lm = denv.engine.local
+    denv.step(iters)
+    denv.sync()
+    mine = (lm.cell_gid[:lm.n_owned].copy(), np.array(denv.env.cells.pdf[:lm.n_owned]), len(denv.engine.peers_recv))
+    denv.close()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    out = None
+    if rank == 0:
+        m, _, cells, faces, nodes, _ = build_problem(nx, ny, scheme)
+        env = fb.Environment(cells, faces, nodes, dtype=real, device=local_dev, reorder="hilbert")
+        env.init()
+        ref = np.array(env.step(iters).cells.pdf)
+        env.close()
+        got = np.zeros_like(ref)
+        for gid, pdf, _ in parts:
+            got[gid] = pdf
+        out = {"bitwise_equal": bool(np.array_equal(got, ref)), "ranks": world, "cells": int(ref.shape[0]),
+               "iterations": iters, "peers_per_rank": [int(p[2]) for p in parts],
+               "what": f"{nx}x{ny}-quad square cut into Hilbert chunks (window-based local meshes), native NCCL path vs one handle on rank 0"}
     dist.barrier()
     return out
 
@@ -218,6 +275,11 @@ def run_reference(args):
 
 
 def workload_config(args, nx, cells, inner):
+    if getattr(args, "mesh", "square") == "porous" and args.impl == "b200":
+        return {"workload": f"porous obstacle field (reference tests/test_bmp.mat outlines, scale {args.porous_scale}), {cells} cells on this GPU, "
+                            f"velocity walls + density inlet/outlet, D2Q9 tau=0.65 dt=0.1, {args.scheme}",
+                "inner_iterations_per_step": inner, "scheme": args.scheme, "l2": "inputs exceed L2 (no flush needed)",
+                "reorder": args.reorder, "partition": args.partition}
     if getattr(args, "scaling", "weak") == "strong" and args.impl == "b200":
         shape = f"fixed global mesh nx={nx} x ny={args.ny_total} quads ({2 * nx * args.ny_total} cells) cut into one strip per GPU"
     else:
@@ -225,7 +287,7 @@ def workload_config(args, nx, cells, inner):
     return {"workload": f"synthetic triangulated square, {shape}, x-periodic + y walls (lid 0.1), D2Q9 tau=0.8 dt=0.1, {args.scheme}",
             "inner_iterations_per_step": inner, "scheme": args.scheme, "l2": "inputs exceed L2 (no flush needed)",
             "reorder": args.reorder, "variant": args.variant, "tile_cells": args.tile, "stages": args.stages,
-            "reverse_sweep": args.reverse, "graph_steps": args.graph}
+            "reverse_sweep": args.reverse, "graph_steps": args.graph, "partition": getattr(args, "partition", "strips")}
 
 
 def main():
@@ -253,9 +315,21 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: nx x nx quads per GPU (default); strong: a fixed nx x ny_total global mesh split into strips")
     ap.add_argument("--ny-total", type=int, default=8944, help="strong scaling: quad rows of the global mesh")
+    ap.add_argument("--partition", default="strips", choices=["strips", "sfc"],
+                    help="N>1: strips = 1-D strips, each rank meshes its own window of the analytic square; sfc = general path: "
+                         "Hilbert-chunk owners from the raw mesh, window-based local meshes (4-6 peers per rank)")
+    ap.add_argument("--mesh", default="square", choices=["square", "porous"],
+                    help="porous: BASELINE configs[2] obstacle field (fixed size -> strong scaling over the GPUs, sfc partition)")
+    ap.add_argument("--porous-scale", type=float, default=8.5)
+    ap.add_argument("--config4", action="store_true",
+                    help="BASELINE configs[4]: the fixed 99 993 920-cell square (2236 x 22360 quads) cut over the GPUs (= --scaling strong --ny-total 22360)")
     ap.add_argument("--torch-exchange", action="store_true",
                     help="N>1: drive the halo exchange from Python with torch.distributed P2P instead of the engine's own NCCL communicator")
     args = ap.parse_args()
+    if args.config4:
+        args.scaling, args.ny_total = "strong", 22360
+    if args.mesh == "porous":
+        args.scaling, args.partition = "strong", "sfc"
     if args.impl == "reference":
         return run_reference(args)
 
@@ -279,15 +353,46 @@ def main():
 
     if args.scaling == "strong" and args.ny_total % world:
         raise SystemExit("--ny-total must be divisible by the number of GPUs")
+    part_stats = None
     if world > 1:
         from fvdbm_jax_b200.distributed import DistributedEnvironment
+        os.environ.setdefault("FVDBM_PLAN_THREADS", str(max(1, len(os.sched_getaffinity(0)) // world)))
         if not args.torch_exchange and not args.no_multi_gpu_check:
-            mg_check = multi_gpu_check(rank, world, local, args.scheme, real)
-        rows = args.nx if args.scaling == "weak" else args.ny_total // world
-        denv = DistributedEnvironment.strips(args.nx, rows, args.scheme, real, rank, world, local,
-                                             native=not args.torch_exchange)
+            mg_check = multi_gpu_check(rank, world, local, args.scheme, real, partition=args.partition)
+        t0 = time.time()
+        if args.mesh == "porous":
+            dyn = fb.D2Q9(tau=0.65, delta_t=0.1)
+            raw, bcs, init = porous_raw_and_callbacks(args.porous_scale, dyn)
+            denv = DistributedEnvironment.from_raw(raw, dyn, args.scheme, real, rank, world, local, bcs, init,
+                                                   native=not args.torch_exchange)
+        elif args.partition == "sfc":
+            dyn = fb.D2Q9(tau=0.8, delta_t=0.1)
+            ny = args.nx * world if args.scaling == "weak" else args.ny_total
+            raw, bcs, init = square_raw_and_callbacks(args.nx, ny, dyn)
+            denv = DistributedEnvironment.from_raw(raw, dyn, args.scheme, real, rank, world, local, bcs, init,
+                                                   native=not args.torch_exchange)
+            del raw
+        else:
+            rows = args.nx if args.scaling == "weak" else args.ny_total // world
+            denv = DistributedEnvironment.strips(args.nx, rows, args.scheme, real, rank, world, local,
+                                                 native=not args.torch_exchange)
+        t_mesh = time.time() - t0
+        part_stats = denv.partition_stats()
         env, n_local, n_global = denv, denv.n_owned, denv.n_global
         stepper = denv
+    elif args.mesh == "porous":
+        dyn = fb.D2Q9(tau=0.65, delta_t=0.1)
+        raw, bcs, init = porous_raw_and_callbacks(args.porous_scale, dyn)
+        m = fb.Mesher()
+        m.import_meshpy(raw)
+        m.calc_mesh_properties()
+        cells, faces, nodes = m.to_env(dyn, flux_method=args.scheme)
+        nodes = bcs(m, nodes)
+        env = fb.Environment(cells, faces, nodes, dtype=real, device=local, reorder=args.reorder)
+        env.init()
+        env.build()
+        n_local = n_global = cells.face_indices.shape[0]
+        stepper = env
     elif args.scaling == "strong":
         # same mesh family as the multi-GPU strips (hash jitter), whole mesh on one GPU
         from fvdbm_jax_b200.distributed import strip_local_mesh, containers_from_mesh
@@ -434,7 +539,12 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
     if mg_check is not None:
         line["multi_gpu_check"] = mg_check
-    if t_mesh is not None:
+    if part_stats is not None:
+        line["partition"] = {"method": args.partition, "peers_per_rank": [p["peers"] for p in part_stats],
+                             "halo_cells_per_rank": [p["halo"] for p in part_stats],
+                             "send_bytes_per_iteration_per_rank": [p["send_bytes_per_iteration"] for p in part_stats],
+                             "owned_cells_per_rank": [p["owned"] for p in part_stats], "local_mesh_build_s": round(t_mesh, 2)}
+    if t_mesh is not None and t_plan is not None:
         line["host_build_s"] = {"mesher": round(t_mesh, 2), "planner_and_upload": round(t_plan, 2)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.scheme, problem) if problem is not None else None

@@ -32,7 +32,7 @@ EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_err
            "fvdbm_set_params",
            "fvdbm_set_option", "fvdbm_info", "fvdbm_check_finite", "fvdbm_halo_set_lists", "fvdbm_halo_pack",
            "fvdbm_halo_unpack", "fvdbm_step_phase", "fvdbm_stream", "fvdbm_comm_unique_id", "fvdbm_comm_init",
-           "fvdbm_halo_set_peers", "fvdbm_plan_create",
+           "fvdbm_halo_set_peers", "fvdbm_sfc_keys", "fvdbm_plan_create",
            "fvdbm_plan_destroy", "fvdbm_plan_array", "fvdbm_plan_scalar")
 
 
@@ -99,6 +99,8 @@ def load():
     lib.fvdbm_halo_set_peers.restype = C.c_int
     lib.fvdbm_stream.argtypes = [H]
     lib.fvdbm_stream.restype = C.c_void_p
+    lib.fvdbm_sfc_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.fvdbm_sfc_keys.restype = C.c_int
     lib.fvdbm_plan_create.argtypes = [C.POINTER(Desc), C.POINTER(P)]
     lib.fvdbm_plan_destroy.argtypes = [P]
     lib.fvdbm_plan_destroy.restype = None

@@ -975,6 +975,35 @@ int fvdbm_halo_set_peers(fvdbm_handle* h, const int32_t* sp, const int64_t* sc, 
     return h ? h->e->halo_set_peers(sp, sc, ns, rp, rc, nr) : FVDBM_ERR_ARG;
 }
 
+// ---- host-only helpers ---------------------------------------------------------------------------
+// Hilbert-curve key of every cell centroid (same curve as reorder.hilbert_index), OpenMP over cells.
+int fvdbm_sfc_keys(const double* points, const int32_t* elements, int64_t ncells, int K, int bits, double lo_x, double lo_y,
+                   double scale, int64_t* keys) {
+    if (!points || !elements || !keys || ncells < 0 || K < 3 || K > 4 || bits < 1 || bits > 30) { g_create_error = "bad argument"; return FVDBM_ERR_ARG; }
+    const int64_t n1 = (int64_t(1) << bits) - 1;
+    const int nthreads = fvdbm::plan_threads();
+    (void)nthreads;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64_t c = 0; c < ncells; ++c) {
+        double cx = 0, cy = 0;
+        for (int k = 0; k < K; ++k) { cx += points[2 * (int64_t)elements[c * K + k]]; cy += points[2 * (int64_t)elements[c * K + k] + 1]; }
+        cx /= K; cy /= K;
+        int64_t x = (int64_t)((cx - lo_x) * scale), y = (int64_t)((cy - lo_y) * scale);
+        x = x < 0 ? 0 : (x > n1 ? n1 : x); y = y < 0 ? 0 : (y > n1 ? n1 : y);
+        int64_t d = 0;
+        for (int64_t s = int64_t(1) << (bits - 1); s > 0; s >>= 1) {
+            const int64_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+            d += s * s * ((3 * rx) ^ ry);
+            if (ry == 0) {
+                if (rx == 1) { x = n1 - x; y = n1 - y; }
+                const int64_t t = x; x = y; y = t;
+            }
+        }
+        keys[c] = d;
+    }
+    return FVDBM_OK;
+}
+
 // ---- host-only planning -------------------------------------------------------------------------
 int fvdbm_plan_create(const fvdbm_desc* desc, fvdbm_plan** out) {
     if (!desc || !out) { g_create_error = "null argument"; return FVDBM_ERR_ARG; }

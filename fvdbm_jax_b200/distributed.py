@@ -239,6 +239,25 @@ class DistributedEnvironment:
         return cls(local, dyn, scheme, dtype, device, n_global=2 * nx * ny_per_rank * world, faces_per_cell=fpc,
                    native=native)
 
+    @classmethod
+    def from_raw(cls, raw, dynamics, scheme, dtype, rank, world, device, boundary_conditions=None, initial_pdf=None,
+                 owner=None, native=True):
+        """General decomposition of an arbitrary raw mesh (points / elements / markers): Hilbert-chunk owners
+        computed from the raw arrays, then only this rank's window is meshed (partition.local_from_raw)."""
+        from .partition import local_from_raw
+        local, fpc = local_from_raw(raw, rank, world, dynamics, scheme, boundary_conditions, initial_pdf, owner)
+        return cls(local, dynamics, scheme, dtype, device, n_global=int(np.asarray(raw.elements).shape[0]),
+                   faces_per_cell=fpc, native=native)
+
+    def partition_stats(self):
+        """Collective: peers / halo sizes / message bytes of every rank (for reports)."""
+        e = self.engine
+        mine = {"owned": int(self.n_owned), "halo": int(e.local.n_local - e.local.n_owned), "peers": len(e.peers_recv),
+                "send_cells": int(e.n_send), "send_bytes_per_iteration": int(e.n_send) * e.Q * np.dtype(self.env.dtype).itemsize}
+        allr = [None] * self.world
+        self.dist.all_gather_object(allr, mine)
+        return allr
+
     # ---- stepping ---------------------------------------------------------------------------------
     def _iterate(self):
         e = self.engine

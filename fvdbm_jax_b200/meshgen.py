@@ -52,7 +52,8 @@ def unique_edges(elements: np.ndarray, num_points: int, alias: Optional[np.ndarr
 
 
 def triangulated_square(nx: int, ny: int, jitter: float = 0.2, seed: int = 0,
-                        periodic_x: bool = False, lx: float | None = None, ly: float | None = None) -> RawMesh:
+                        periodic_x: bool = False, lx: float | None = None, ly: float | None = None,
+                        with_faces: bool = True) -> RawMesh:
     """``nx x ny`` unit quads, interior vertices jittered by U(-jitter, jitter)^2, each quad split
     along alternating diagonals ((i+j)%2), triangles counter-clockwise.
 
@@ -96,7 +97,8 @@ def triangulated_square(nx: int, ny: int, jitter: float = 0.2, seed: int = 0,
         ids = np.arange((nx + 1) * (ny + 1), dtype=np.int32).reshape(ny + 1, nx + 1)
         ids[:, -1] = ids[:, 0]
         alias = ids.reshape(-1)
-    faces = unique_edges(elements, points.shape[0], alias)
+    # with_faces=False: points + elements only (what the window-based decomposition needs from a global mesh)
+    faces = unique_edges(elements, points.shape[0], alias) if with_faces else np.zeros((0, 2), dtype=np.int32)
     return RawMesh(points, elements, faces, markers.reshape(-1), alias, (nx, ny))
 
 

@@ -26,7 +26,7 @@ import numpy as np
 from .reorder import hilbert_index, hilbert_perm, order_to_perm
 
 __all__ = ["GlobalMesh", "LocalMesh", "partition_sfc", "partition_strips", "partition_rcm", "partition_cells",
-           "refine_partition",
+           "refine_partition", "sfc_owner_from_raw", "window_from_raw", "local_from_raw",
            "extract_local", "exchange_lists", "edge_cut"]
 
 
@@ -133,12 +133,14 @@ def edge_cut(stencil: np.ndarray, part: np.ndarray) -> int:
     return int(np.count_nonzero(part[stencil[m, 0]] != part[stencil[m, 1]]))
 
 
-def refine_partition(stencil: np.ndarray, part: np.ndarray, nparts: int, sweeps: int = 4,
+def refine_partition(stencil: np.ndarray, part: np.ndarray, nparts: int, sweeps: int = 8,
                      imbalance: float = 1.03) -> np.ndarray:
-    """METIS-style boundary refinement (greedy gain moves under a balance constraint): a cell moves
-    to the neighbouring part that holds the majority of its face neighbours if that reduces the
-    edge cut and keeps every part below ``imbalance`` x the mean size."""
-    part = part.copy()
+    """METIS-style boundary refinement, fully vectorised (no per-cell Python loop): per sweep every
+    boundary cell computes the gain of moving to the neighbouring part that holds most of its face
+    neighbours; the candidates that are strict local maxima of (gain, -id) among their face neighbours
+    form an independent set, so all of them move at once with their gains still valid; per target part
+    the moves are admitted in order of decreasing gain up to ``imbalance`` x the mean size."""
+    part = np.array(part, dtype=np.int32, copy=True)
     n = part.shape[0]
     m = (stencil[:, 0] >= 0) & (stencil[:, 1] >= 0)
     a = np.concatenate([stencil[m, 0], stencil[m, 1]]).astype(np.int64)
@@ -146,42 +148,49 @@ def refine_partition(stencil: np.ndarray, part: np.ndarray, nparts: int, sweeps:
     cap = int(imbalance * n / nparts) + 1
     for _ in range(sweeps):
         pa, pb = part[a], part[b]
-        # neighbours per (cell, part) via a sparse count
-        key = a * nparts + pb
+        cut = pa != pb
+        if not cut.any():
+            break
+        # neighbours per (boundary cell, foreign part) and per (boundary cell, own part)
+        bc = np.unique(a[cut])
+        on_b = np.zeros(n, dtype=bool)
+        on_b[bc] = True
+        sel = on_b[a]
+        key = a[sel] * nparts + pb[sel]
         uk, cnt = np.unique(key, return_counts=True)
         cell, prt = uk // nparts, (uk % nparts).astype(np.int32)
-        own_cnt = np.zeros(n, dtype=np.int64)
         own = prt == part[cell]
+        own_cnt = np.zeros(n, dtype=np.int64)
         own_cnt[cell[own]] = cnt[own]
         gain = cnt - own_cnt[cell]
         cand = (~own) & (gain > 0)
         if not cand.any():
             break
-        # best target per cell
-        order = np.lexsort((-gain[cand], cell[cand]))
+        order = np.lexsort((-gain[cand], cell[cand]))                 # best target per cell first
         c_s, p_s, g_s = cell[cand][order], prt[cand][order], gain[cand][order]
         first = np.ones(c_s.shape[0], dtype=bool)
         first[1:] = c_s[1:] != c_s[:-1]
         c_s, p_s, g_s = c_s[first], p_s[first], g_s[first]
-        # apply highest gains first while respecting capacities; skip cells adjacent to an already
-        # moved cell in this sweep (their gains are stale)
-        sizes = np.bincount(part, minlength=nparts).astype(np.int64)
-        moved = np.zeros(n, dtype=bool)
-        touched = np.zeros(n, dtype=bool)
-        nbr_start = np.searchsorted(a[np.argsort(a, kind="stable")], np.arange(n + 1))
-        nbr = b[np.argsort(a, kind="stable")]
-        for i in np.argsort(-g_s, kind="stable"):
-            c, p = int(c_s[i]), int(p_s[i])
-            if touched[c] or sizes[p] + 1 > cap:
-                continue
-            sizes[part[c]] -= 1
-            sizes[p] += 1
-            part[c] = p
-            moved[c] = True
-            touched[c] = True
-            touched[nbr[nbr_start[c]:nbr_start[c + 1]]] = True
-        if not moved.any():
+        # independent set: drop a candidate if a face neighbour is a stronger candidate
+        g_of = np.zeros(n, dtype=np.int64)
+        g_of[c_s] = g_s
+        ga, gb = g_of[a], g_of[b]
+        weaker = (gb > ga) | ((gb == ga) & (gb > 0) & (b < a))
+        blocked = np.bincount(a[weaker], minlength=n) > 0
+        keep = ~blocked[c_s]
+        c_m, p_m, g_m = c_s[keep], p_s[keep], g_s[keep]
+        if c_m.size == 0:
             break
+        # capacity: per target part admit the highest gains while it stays below the cap (departures ignored)
+        sizes = np.bincount(part, minlength=nparts).astype(np.int64)
+        o = np.lexsort((c_m, -g_m, p_m))
+        c_m, p_m = c_m[o], p_m[o]
+        start = np.searchsorted(p_m, np.arange(nparts), side="left")
+        rank_in = np.arange(c_m.size) - start[p_m]
+        ok = rank_in < (cap - sizes)[p_m]
+        if not ok.any():
+            break
+        part[c_m[ok]] = p_m[ok]
     return part
 
 
@@ -257,6 +266,94 @@ def extract_local(g: GlobalMesh, part: np.ndarray, rank: int, reorder: bool = Tr
         perm = np.concatenate([p_owned, np.arange(No, Nl, dtype=np.int32)]).astype(np.int32)
     return LocalMesh(rank, No, gid_of[cells_l].astype(np.int64), part[halo].astype(np.int32), faces_l.astype(np.int64),
                      nodes_l.astype(np.int64), complete, local, perm)
+
+
+# ---------------------------------------------------------------------------------------------------
+# scalable path: a rank's local mesh from a WINDOW of the raw mesh (nobody builds the global mesh)
+# ---------------------------------------------------------------------------------------------------
+def sfc_owner_from_raw(points: np.ndarray, elements: np.ndarray, nparts: int, bits: int = 16) -> np.ndarray:
+    """Owner rank of every cell = balanced chunks of the Hilbert curve through the cell centroids, computed
+    from the raw mesh (points, elements): O(N) keys (native OpenMP helper fvdbm_sfc_keys) + an O(N) selection
+    of the nparts-1 splitters (np.partition) instead of a global sort.  Deterministic, identical on every rank."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n = elements.shape[0]
+    lo = pts.min(axis=0)
+    scale = ((1 << bits) - 1) / max(float((pts.max(axis=0) - lo).max()), 1e-300)
+    keys = np.empty(n, dtype=np.int64)
+    from . import _lib
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    _lib.check(_lib.load().fvdbm_sfc_keys(pts.ctypes.data, el.ctypes.data, n, int(el.shape[1]), bits, float(lo[0]), float(lo[1]),
+                                          float(scale), keys.ctypes.data))       # host-only C/OpenMP helper (no GPU)
+    # ties (equal keys) are broken by cell id so that the chunks are exactly balanced
+    keys = keys * np.int64(n) + np.arange(n, dtype=np.int64) if n < (1 << 31) else keys
+    cuts = [(n * r) // nparts for r in range(1, nparts)]
+    if not cuts:
+        return np.zeros(n, dtype=np.int32)
+    split = np.partition(keys, cuts)[cuts]
+    return np.searchsorted(split, keys, side="right").astype(np.int32)
+
+
+def window_from_raw(raw, owner: np.ndarray, rank: int, chunk: int = 1 << 22):
+    """Raw sub-mesh a rank needs: its owned cells plus every cell sharing a (canonical) vertex with one of
+    them -- a superset of the face neighbours and of the rings of the boundary nodes of owned cells.  Window
+    cells keep ascending global ids, so shared faces get the same orientation / stencil order in every rank's
+    window and cut faces are evaluated from bit-identical coefficients on both sides."""
+    from .meshgen import RawMesh, unique_edges
+    el = np.asarray(raw.elements)
+    alias = getattr(raw, "point_alias", None)
+    canon = (lambda ids: ids) if alias is None else (lambda ids: alias[ids])
+    P = raw.points.shape[0]
+    vmark = np.zeros(P, dtype=bool)
+    owned = np.nonzero(owner == rank)[0]
+    vmark[canon(el[owned]).reshape(-1)] = True
+    touch = []
+    for c0 in range(0, el.shape[0], chunk):
+        t = vmark[canon(el[c0:c0 + chunk])].any(axis=1)
+        touch.append(np.nonzero(t)[0] + c0)
+    window = np.concatenate(touch) if touch else np.zeros(0, dtype=np.int64)
+    el_w = el[window]
+    used_ids = el_w.reshape(-1) if alias is None else np.concatenate([el_w.reshape(-1), alias[el_w.reshape(-1)]])
+    used = np.zeros(P, dtype=bool)
+    used[used_ids] = True
+    remap = -np.ones(P, dtype=np.int64)
+    pid = np.nonzero(used)[0]
+    remap[pid] = np.arange(pid.shape[0])
+    el_l = remap[el_w].astype(np.int32)
+    alias_l = None if alias is None else remap[alias[pid]].astype(np.int32)
+    faces = unique_edges(el_l, pid.shape[0], alias_l)
+    w = RawMesh(np.asarray(raw.points)[pid], el_l, faces, np.asarray(raw.point_markers)[pid], alias_l, None)
+    w.cell_gid = window.astype(np.int64)
+    w.point_gid = pid.astype(np.int64)
+    return w
+
+
+def local_from_raw(raw, rank: int, nparts: int, dynamics, scheme: str, boundary_conditions=None, initial_pdf=None,
+                   owner: Optional[np.ndarray] = None, dim_multiplier=1):
+    """General, scalable decomposition (north_star: "the Mesher partitions cells ... across the 8 B200s"):
+    owner ranks from the raw mesh (Hilbert chunks unless given), then THIS rank's window -> Mesher -> containers
+    -> ``extract_local``.  Cost per rank is O(N) cheap passes over the raw arrays plus the Mesher on
+    ~N/nparts cells; no rank ever holds the global connectivity.
+
+    ``boundary_conditions(mesher, nodes) -> nodes`` applies the BC setters, ``initial_pdf(mesher) -> (n,Q)``
+    the start populations (both see only the window).  Returns (LocalMesh, faces_per_owned_cell)."""
+    from .mesher import Mesher
+    if owner is None:
+        owner = sfc_owner_from_raw(raw.points, raw.elements, nparts)
+    w = window_from_raw(raw, owner, rank)
+    m = Mesher()
+    m.import_meshpy(w)
+    m.calc_mesh_properties()
+    cells, faces, nodes = m.to_env(dynamics, flux_method=scheme, dim_multiplier=dim_multiplier)
+    if boundary_conditions is not None:
+        nodes = boundary_conditions(m, nodes)
+    if initial_pdf is not None:
+        cells.pdf = initial_pdf(m)
+    g = GlobalMesh.from_containers(cells, faces, nodes)
+    g.cell_gid = w.cell_gid
+    part_w = owner[w.cell_gid]
+    local = extract_local(g, part_w, rank, reorder=True)
+    owned_faces = np.unique(g.face_indices[part_w == rank].reshape(-1)).size
+    return local, owned_faces / max(1, local.n_owned)
 
 
 def exchange_lists(local: LocalMesh, requests_from_peers: Dict[int, np.ndarray]):

@@ -208,6 +208,12 @@ int  fvdbm_comm_init(fvdbm_handle* h, int nranks, int rank, const void* id);
 int  fvdbm_halo_set_peers(fvdbm_handle* h, const int32_t* send_peers, const int64_t* send_counts, int n_send_peers,
                           const int32_t* recv_peers, const int64_t* recv_counts, int n_recv_peers);
 
+/* ---- host-only decomposition helper (no GPU needed): Hilbert-curve key of every cell centroid of a raw mesh
+ * (points [P*2] f64, elements [ncells*K] i32), centroid -> integer grid by (c - lo) * scale, `bits` per axis;
+ * OpenMP over cells (FVDBM_PLAN_THREADS).  Used by partition.sfc_owner_from_raw for 10^8-cell meshes. */
+int  fvdbm_sfc_keys(const double* points, const int32_t* elements, int64_t ncells, int K, int bits,
+                    double lo_x, double lo_y, double scale, int64_t* keys_out);
+
 /* ---- host-only planning (no GPU needed): builds the device layout from a desc so that the
  * layout logic is unit-testable on CPU.  key = name of a plan array, see csrc/plan.hpp. */
 typedef struct fvdbm_plan fvdbm_plan;

@@ -170,3 +170,74 @@ def test_mesher_partition_front_door(method):
         assert extract_local(g, part, r).n_owned == sizes[r]
     with pytest.raises(ValueError):
         m.partition(4, method="metis5")
+
+
+def _side_table(local):
+    """{(owned gid, k): (neighbour gid or -1, sign, slot, n, L, d0, d1, node types of the face)} of a LocalMesh."""
+    g = local.mesh
+    out = {}
+    for c in range(local.n_owned):
+        for k in range(g.face_indices.shape[1]):
+            j = g.face_indices[c, k]
+            a, b = g.stencil[j]
+            slot = 0 if a == c else 1
+            o = b if slot == 0 else a
+            out[(int(local.cell_gid[c]), k)] = (int(local.cell_gid[o]) if o >= 0 else -1, int(g.face_signs[c, k]), slot,
+                                                tuple(g.n[j]), float(g.L[j, 0]), tuple(g.stencil_dists[j]),
+                                                tuple(int(g.node_type[p, 0]) for p in g.nodes_index[j]))
+    return out
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("nparts", [2, 5])
+def test_window_based_local_mesh_equals_extraction_from_the_global_mesh(periodic, nparts):
+    """partition.local_from_raw builds a rank's local mesh from a window of the RAW mesh (owned cells + vertex
+    ring) without ever meshing the whole domain: owned / halo sets, every side record of every owned cell
+    (bit for bit) and the initial state must equal what extract_local derives from the global mesh."""
+    from fvdbm_jax_b200.partition import local_from_raw, sfc_owner_from_raw
+    nx, ny = 16, 11
+    raw = meshgen.triangulated_square(nx, ny, seed=3, periodic_x=periodic)
+    m, dyn, g = problem(nx, ny, periodic=periodic)
+    owner = sfc_owner_from_raw(raw.points, raw.elements, nparts)
+    sizes = np.bincount(owner, minlength=nparts)
+    assert sizes.max() - sizes.min() <= 1
+
+    def bcs(mm, nodes):
+        for mk in ((1,) if periodic else (1, 2, 4)):
+            nodes = mm.set_vel_node(nodes, mk, np.array([0.0, 0.0]))
+        return mm.set_vel_node(nodes, 3, np.array([0.1, 0.0]))
+
+    for r in range(nparts):
+        ref = extract_local(g, owner, r)
+        loc, fpc = local_from_raw(raw, r, nparts, dyn, "lax_wendroff", boundary_conditions=bcs, owner=owner)
+        assert loc.n_owned == ref.n_owned and np.array_equal(loc.cell_gid, ref.cell_gid)
+        assert np.array_equal(loc.halo_owner, ref.halo_owner)
+        assert _side_table(loc) == _side_table(ref)
+        assert np.array_equal(loc.mesh.cell_pdf, ref.mesh.cell_pdf)
+        # active (complete) boundary nodes carry identical rings: same ring cells (as global ids) and distances
+        def rings(l):
+            out = {}
+            for p in np.nonzero(l.node_complete)[0]:
+                ok = (l.mesh.ring[p] >= 0) & (l.mesh.ring_dists[p] > 0)
+                key = tuple(sorted(l.cell_gid[l.mesh.ring[p][ok]].tolist()))
+                out[key] = (int(l.mesh.node_type[p, 0]), tuple(sorted(l.mesh.ring_dists[p][ok].tolist())), tuple(l.mesh.node_vel[p]))
+            return out
+        assert rings(loc) == rings(ref)
+        assert 1.4 < fpc < 2.0
+
+
+def test_vectorised_refinement_on_a_larger_mesh_is_fast():
+    import time
+    raw = meshgen.triangulated_square(300, 300, seed=1)
+    m = fb.Mesher(); m.import_meshpy(raw); m.calc_mesh_properties()
+    st = np.asarray(m.face_cell_indices)
+    part = partition_sfc(m.cell_centers, 8)
+    rng = np.random.default_rng(0)
+    noisy = part.copy()
+    flip = rng.random(part.size) < 0.02
+    noisy[flip] = rng.integers(0, 8, int(flip.sum()))
+    t0 = time.time()
+    ref = refine_partition(st, noisy, 8)
+    assert time.time() - t0 < 20.0
+    assert edge_cut(st, ref) < 0.5 * edge_cut(st, noisy)
+    assert np.bincount(ref, minlength=8).max() <= int(1.03 * part.size / 8) + 1
