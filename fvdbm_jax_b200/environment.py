@@ -16,6 +16,9 @@ jit.  Differences a caller can observe:
   and the reference's shapes, with the reference's one-step lag for rho / vel / pdf_eq / flux
   (SURVEY.md A.2).
 * precision is explicit: ``Environment.dtype`` / ``dtype=`` (float32 like stock JAX, or float64).
+* optional ``cells.inv_area`` (N,) attribute: 1/area of every cell multiplying the flux divergence (the
+  physically consistent finite-volume update on non-unit cells).  Absent = the reference's behaviour, which
+  has no area anywhere (reference containers.py:115-121); ``Mesher.cell_inv_areas()`` computes it.
 * no CPU fallback: without the CUDA library or a CUDA device ``step()`` raises.
 """
 from __future__ import annotations
@@ -74,6 +77,7 @@ class _View:
 class _CellsView(_View):
     _dynamic = {"pdf": "cells.pdf", "rho": "cells.rho", "vel": "cells.vel", "pdf_eq": "cells.pdf_eq"}
     _static = ("face_indices", "face_normals")
+    _optional = ("inv_area",)
 
 
 class _FacesView(_View):
@@ -197,7 +201,8 @@ class Environment:
             face_dists=_np(f.stencil_dists), face_node_idx=_np(f.nodes_index), face_n=_np(f.n), face_L=face_L,
             node_type=_np(n.type), node_cell_idx=_np(n.cells_index), node_cell_dist=_np(n.cell_dists),
             cell_pdf=host["cells.pdf"], node_pdf=host["nodes.pdf"], node_rho=host["nodes.rho"],
-            node_vel=host["nodes.vel"], cell_perm=perm, n_owned=self._n_owned, device_id=self.device, mode=mode)
+            node_vel=host["nodes.vel"], cell_perm=perm, n_owned=self._n_owned, device_id=self.device, mode=mode,
+            cell_inv_area=None if getattr(c, "inv_area", None) is None else _np(c.inv_area).reshape(-1))
 
     def build(self):
         """Create the device engine (done implicitly by the first ``step``)."""

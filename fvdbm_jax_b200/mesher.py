@@ -284,6 +284,14 @@ class Mesher:
         nodes.rho[m] = rho
         return nodes
 
+    def cell_inv_areas(self, dim_multiplier=1):
+        """1 / area of every cell (extension, not in the reference): assign to ``cells.inv_area`` for the
+        physically consistent update f += dt((feq - f)/tau - (1/A) sum_k s_k flux_k)."""
+        p = self.points[self.cells]
+        area = 0.5 * np.abs((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1])
+                            - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1]))
+        return 1.0 / (area * dim_multiplier * dim_multiplier)
+
     # ------------------------------------------------------------------ decomposition
     def partition(self, nparts: int, method: str = "auto", refine: bool = True):
         """Owner rank of every cell for a multi-GPU run (north_star: "the Mesher partitions cells ...

@@ -78,6 +78,7 @@ class StepOracle:
         self.ring = i(static["nodes.cells_index"])                    # (P,M), -1 padded
         self.ring_d = f(static["nodes.cell_dists"])                   # (P,M), -1 padded
         self.pdf = f(state["cells.pdf"])
+        self.inv_area = None if static.get("cells.inv_area") is None else f(static["cells.inv_area"]).reshape(-1)
         N, P = self.pdf.shape[0], self.type.shape[0]
         self.rho = f(state.get("cells.rho", np.zeros((N, 1))))
         self.vel = f(state.get("cells.vel", np.zeros((N, 2))))
@@ -153,6 +154,8 @@ class StepOracle:
     def cells(self):                                                  # S5
         fl = self.flux[self.face_indices] * self.face_signs[..., None].astype(self.dtype)
         total = np.sum(fl, axis=1)
+        if self.inv_area is not None:      # optional physically consistent mode (NOT in the reference, containers.py:115-121)
+            total = total * self.inv_area[:, None]
         self.pdf = self.pdf + self.delta_t * (1 / self.tau * (self.pdf_eq - self.pdf) - total)
 
     def step(self, n: int = 1):

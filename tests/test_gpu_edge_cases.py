@@ -202,3 +202,37 @@ def test_async_transfers_match_blocking_ones():
     with pytest.raises(ValueError, match="ticket"):
         env.wait(10 ** 6)
     env.close(); ref.close()
+
+
+@pytest.mark.parametrize("mode", ["fused", "staged"])
+@pytest.mark.parametrize("scheme", ["lax_wendroff", "upwind"])
+def test_optional_inverse_area_mode_matches_the_numpy_oracle(scheme, mode):
+    """fvdbm_desc.cell_inv_area: the flux divergence of every cell is scaled by 1/area.  NULL is
+    the reference's behaviour (every other test); here the engine is compared with the NumPy oracle's switch."""
+    raw = meshgen.triangulated_square(18, 12, seed=5, lx=9.0, ly=7.0)          # non-unit cells
+    m = fb.Mesher()
+    m.import_meshpy(raw)
+    m.calc_mesh_properties()
+    dyn = fb.D2Q9(tau=0.8, delta_t=0.02)
+    cells, faces, nodes = m.to_env(dyn, flux_method=scheme)
+    for mk in (1, 2, 4):
+        nodes = m.set_vel_node(nodes, mk, np.array([0.0, 0.0]))
+    nodes = m.set_vel_node(nodes, 3, np.array([0.05, 0.0]))
+    cells.inv_area = m.cell_inv_areas()
+    assert cells.inv_area.min() > 2.0                                          # areas ~0.15: the factor matters
+    static = {"cells.face_indices": cells.face_indices, "cells.face_normals": cells.face_normals,
+              "faces.nodes_index": faces.nodes_index, "faces.stencil_cells_index": faces.stencil_cells_index,
+              "faces.stencil_dists": faces.stencil_dists, "faces.n": faces.n, "faces.L": faces.L,
+              "nodes.type": nodes.type, "nodes.cells_index": nodes.cells_index, "nodes.cell_dists": nodes.cell_dists,
+              "cells.inv_area": cells.inv_area}
+    state = {"cells.pdf": cells.pdf, "nodes.pdf": nodes.pdf, "nodes.rho": nodes.rho, "nodes.vel": nodes.vel}
+    o = StepOracle(static, state, 9, dyn.tau, dyn.delta_t, scheme, np.float64).step(40)
+    plain = StepOracle({k: v for k, v in static.items() if k != "cells.inv_area"}, state, 9, dyn.tau, dyn.delta_t, scheme,
+                       np.float64).step(40)
+    assert np.max(np.abs(o.pdf - plain.pdf)) > 1e-4                            # the switch changes the physics
+    env = fb.Environment(cells, faces, nodes, dtype=np.float64, mode=mode)
+    env.init()
+    env = env.step(40)
+    for name, ref in (("pdf", o.pdf), ("rho", o.rho), ("vel", o.vel)):
+        assert golden.rel_err(getattr(env.cells, name), ref) < 1e-10, name
+    env.close()
