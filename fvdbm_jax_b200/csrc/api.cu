@@ -121,6 +121,19 @@ struct DevBuf {
 
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// launch with (pdl = true) or without the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename real, int Q, int K, int SCHEME>
 struct EngineT final : Engine {
     Plan<real> plan;
@@ -133,6 +146,7 @@ struct EngineT final : Engine {
     int mode = FVDBM_MODE_FUSED;
     int variant = FVDBM_VARIANT_DIRECT;   // fp32: PAIR (two cells per thread, packed math); fp64: DIRECT; TMA is opt-in
     int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
+    int pdl = 0;                         // programmatic dependent launch chain (default: on below 1M cells)
     int prefetch_dist = 296;             // CTAs of L2 look-ahead (0.4 of a resident wave); measured on B200: burst 0.231 -> 0.194 ms per
                                          // 10M-cell iteration, sustained +2-3 % (profiles/r2_ab_pair_kernel.jsonl)
     int num_sms = 148;
@@ -281,7 +295,8 @@ struct EngineT final : Engine {
         if (const char* e = getenv("FVDBM_TILE_CELLS")) tile_cells = atoi(e);
         if (const char* e = getenv("FVDBM_STAGES")) stages = atoi(e);
         // latency-bound meshes: batch iterations in CUDA graphs by default (20k cells: 13.2 -> 7.2 us/step)
-        if (plan.No < 1000000) graph_steps = 50;      // (at 2M cells graphs measured slightly slower: 70.9 vs 65.5 us)
+        if (plan.No < 1000000) { graph_steps = 50; pdl = 1; }      // (at 2M cells graphs measured slightly slower: 70.9 vs 65.5 us)
+        if (const char* e = getenv("FVDBM_PDL")) pdl = atoi(e) ? 1 : 0;
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
@@ -338,7 +353,7 @@ struct EngineT final : Engine {
         const int64_t count = plan.NA;
         if (count == 0) return FVDBM_OK;
         NodeArgs<real> a = node_args(count);
-        k_nodes<real, Q><<<blocks_for(count * 32, 256), 256, 0, stream>>>(a);
+        CU_TRY(launch_k(k_nodes<real, Q>, blocks_for(count * 32, 256), 256, 0, stream, pdl_chain(), a));
         ++launches;
         CU_TRY(cudaGetLastError());
         return FVDBM_OK;
@@ -350,7 +365,7 @@ struct EngineT final : Engine {
         if (variant == FVDBM_VARIANT_PAIR) {
             launch_pair(a, end - begin, st);
         } else if (variant == FVDBM_VARIANT_DIRECT) {
-            k_fused_direct<real, Q, K, SCHEME><<<blocks_for(end - begin, 256), 256, 0, st>>>(a);
+            CU_TRY(launch_k(k_fused_direct<real, Q, K, SCHEME>, blocks_for(end - begin, 256), 256, 0, st, pdl_chain(), a));
         } else {
             const size_t smem = kTmaHeader + (size_t)stages * stage_bytes(tile_cells);
             int per_sm = ctas_per_sm;
@@ -364,7 +379,7 @@ struct EngineT final : Engine {
             const int64_t ntiles = (end - begin) / tile_cells;
             int64_t grid = (int64_t)num_sms * per_sm;
             if (grid > ntiles) grid = ntiles;
-            k_fused_tma<real, Q, K, SCHEME><<<(unsigned)grid, tile_cells, smem, st>>>(a, stages);
+            CU_TRY(launch_k(k_fused_tma<real, Q, K, SCHEME>, (unsigned)grid, (unsigned)tile_cells, smem, st, pdl_chain(), a, stages));
         }
         ++launches;
         CU_TRY(cudaGetLastError());
@@ -373,7 +388,7 @@ struct EngineT final : Engine {
 
     // fp32 only: two cells per thread, 128 threads (= 256 cells) per CTA
     void launch_pair(const FusedArgs<float>& a, int64_t cells, cudaStream_t st) {
-        k_fused_pair<Q, K, SCHEME><<<blocks_for(cells / 2, FVDBM_PAIR_THREADS), FVDBM_PAIR_THREADS, 0, st>>>(a);
+        launch_k(k_fused_pair<Q, K, SCHEME>, blocks_for(cells / 2, FVDBM_PAIR_THREADS), FVDBM_PAIR_THREADS, 0, st, pdl_chain(), a);
     }
     void launch_pair(const FusedArgs<double>&, int64_t, cudaStream_t) {}
 
@@ -433,8 +448,19 @@ struct EngineT final : Engine {
 
     // One iteration: interior cells run concurrently with [node kernel -> border cells]; the caller may
     // have issued the interior part earlier (step_phase(0)) to overlap it with a halo exchange.
+    // Latency-bound meshes: ONE stream, [node kernel -> all cells] per iteration, every launch programmatically
+    // dependent on the previous one (PDL) so launch latency and the kernels' prologues (index math, streaming loads)
+    // overlap the predecessor's tail.  Bandwidth-bound meshes keep the two-stream overlap schedule below.
+    bool pdl_chain() const { return pdl && mode == FVDBM_MODE_FUSED && !native_exchange() && plan.No == plan.N && !phase0_done; }
+
     int step_fused_once() {
         int rc;
+        if (pdl_chain()) {
+            if ((rc = launch_nodes())) return rc;
+            if ((rc = launch_fused(0, owned_end(), stream))) return rc;
+            prev = cur; cur = nxt(); ++steps;
+            return FVDBM_OK;
+        }
         const bool xchg = native_exchange();
         if (xchg && phase0_done) { err = "step_phase(0) cannot be combined with the native exchange"; return FVDBM_ERR_STATE; }
         if (!phase0_done && (rc = fork_interior())) return rc;       // fork first: the exchange must not delay it
@@ -567,6 +593,7 @@ struct EngineT final : Engine {
     int64_t launches_per_step() const {
         if (mode == FVDBM_MODE_STAGED) return 3 + (plan.NA > 0 ? 1 : 0);
         // own kernels only: the grouped ncclSend/Recv of a native exchange is NCCL's launch, not counted
+        if (pdl_chain()) return (plan.NA > 0 ? 1 : 0) + 1;
         return (plan.NA > 0 ? 1 : 0) + (plan.Bstart > 0 ? 1 : 0) + (owned_end() > plan.Bstart ? 1 : 0) +
                (native_exchange() ? (halo_send.n ? 1 : 0) + (halo_recv.n ? 1 : 0) : 0);
     }
@@ -787,6 +814,7 @@ struct EngineT final : Engine {
         case FVDBM_OPT_GRAPH_STEPS: graph_steps = (int)v; break;
         case FVDBM_OPT_CTAS_PER_SM: ctas_per_sm = (int)v; break;
         case FVDBM_OPT_REVERSE_SWEEP: reverse_sweep = v ? 1 : 0; break;
+        case FVDBM_OPT_PDL: pdl = v ? 1 : 0; break;
         case FVDBM_OPT_PREFETCH_DIST: if (v < 0 || v > (1 << 20)) { err = "prefetch distance out of range"; return FVDBM_ERR_ARG; } prefetch_dist = (int)v; break;
         case FVDBM_OPT_TEMPORAL:
             if (v) { err = "temporal blocking was removed in ABI 2 (measured slower than the single-step kernel; DESIGN.md)"; return FVDBM_ERR_UNSUPPORTED; }

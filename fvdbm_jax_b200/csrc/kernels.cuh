@@ -35,6 +35,13 @@ struct FusedArgs {
 #define FVDBM_PAIR_MINCTAS 5          // A/B on B200 (profiles/r2_ab_pair_kernel.jsonl): 128x5 (96 regs) beats 128x4, 128x6 (spills),
 #endif                                // 256x2 and 64x8 in both the burst and the power-capped sustained regime
 
+// Programmatic dependent launch (PDL): a kernel launched with programmaticStreamSerialization may start while its
+// predecessor in the stream is still running; it must pass pdl_wait() before touching anything the predecessor
+// writes.  Every kernel triggers its own dependents only AFTER its wait, so at any time at most two consecutive
+// kernels overlap and everything older is complete.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -89,6 +96,10 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     for (int q = 0; q < Q; ++q) f[q] = __ldg(gp + q * kTW);
     const bool live = code[0] != kHole;
     if (!live) code[0] = 0;                        // neutral: interior side towards position 0
+    // PDL: everything above reads data older than the predecessor (the node kernel); only the ghost sides below read
+    // what it writes.  The streaming loads stay in flight across the wait.
+    pdl_wait();
+    pdl_trigger();
     const real* pin = a.pdf_in;
     auto gather = [pin](int64_t nb, real* fn) {
         const real* pn = pin + pdf_index<Q>(nb);
@@ -140,6 +151,8 @@ __global__ void __launch_bounds__(FVDBM_PAIR_THREADS, FVDBM_PAIR_MINCTAS) k_fuse
     const bool live0 = code[0].x != kHole, live1 = code[0].y != kHole;
     if (!live0) code[0].x = 0;                     // neutral: interior side towards position 0
     if (!live1) code[0].y = 0;
+    pdl_wait();                                    // see k_fused_direct
+    pdl_trigger();
     const float* pin = a.pdf_in;
     auto gather = [pin](int64_t nb, float* fn) {
         const float* pn = pin + pdf_index<Q>(nb);
@@ -258,6 +271,8 @@ __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, cons
         for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
         fence_barrier_init();
     }
+    pdl_wait();
+    pdl_trigger();
     __syncthreads();
     const int64_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
     if (tid == 0)
@@ -379,6 +394,8 @@ template <typename real, int Q>
 __global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
     const int node = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_wait();                                    // the ring gathers read the populations the previous cell kernel wrote
+    pdl_trigger();
     if (node >= a.NA) return;
     real rho_n, ux_n, uy_n, pdf_n[Q];
     warp_eval_node<real, Q>(a, node, lane, rho_n, ux_n, uy_n, pdf_n);

@@ -155,6 +155,10 @@ def test_fused_variants_bitwise_identical():
                dict(variant=_lib.VARIANT_DIRECT, reverse=1, graph=2, reorder="hilbert"),
                dict(variant=_lib.VARIANT_TMA, tile=128, stages=4, reorder="rcm", ctas=1)]
     configs.append(dict(variant=_lib.VARIANT_PAIR, reverse=1, graph=6, reorder="rcm"))
+    # schedules: two-stream overlap (pdl=0) vs single-stream programmatic-dependent-launch chain (pdl=1), with / without graphs
+    configs += [dict(variant=_lib.VARIANT_DIRECT, pdl=0), dict(variant=_lib.VARIANT_DIRECT, pdl=0, graph=8),
+                dict(variant=_lib.VARIANT_DIRECT, pdl=1, graph=8), dict(variant=_lib.VARIANT_PAIR, pdl=1, graph=0),
+                dict(variant=_lib.VARIANT_TMA, tile=128, stages=2, pdl=1, graph=4)]
     for cfg in configs:
         env = fb.Environment(cells, faces, nodes, dtype=np.float32, reorder=cfg.get("reorder", "none"))
         env.init()
@@ -163,6 +167,8 @@ def test_fused_variants_bitwise_identical():
             env.set_option(_lib.OPT_TILE_CELLS, cfg["tile"]).set_option(_lib.OPT_STAGES, cfg["stages"])
         env.set_option(_lib.OPT_REVERSE_SWEEP, cfg.get("reverse", 0)).set_option(_lib.OPT_GRAPH_STEPS, cfg.get("graph", 0))
         env.set_option(_lib.OPT_CTAS_PER_SM, cfg.get("ctas", 0))
+        if "pdl" in cfg:
+            env.set_option(_lib.OPT_PDL, cfg["pdl"])
         env = env.step(37)
         got = (env.cells.pdf.copy(), env.nodes.pdf.copy(), env.cells.rho.copy())
         if ref is None:

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--variants", default="0", help="comma list of FVDBM_VARIANT_* (0 = the engine's default)")
     ap.add_argument("--prefetch", default="-1", help="comma list of L2 prefetch distances (-1 = default)")
+    ap.add_argument("--pdl", default="-1", help="comma list: 0 two-stream schedule, 1 PDL chain (-1 = default)")
     args = ap.parse_args()
     def built():
         name, (cells, faces, nodes) = quad_ldc()
@@ -45,8 +46,11 @@ def main():
         n = np.asarray(cells.face_indices).shape[0]
         env = fb.Environment(cells, faces, nodes, dtype=np.float32)
         env.init(); env.build()
-        combos = [(int(g), int(v), int(pf)) for g in args.graphs.split(",") for v in args.variants.split(",") for pf in args.prefetch.split(",")]
-        for g, variant, pf in combos:
+        combos = [(int(g), int(v), int(pf), int(pd)) for g in args.graphs.split(",") for v in args.variants.split(",")
+                  for pf in args.prefetch.split(",") for pd in args.pdl.split(",")]
+        for g, variant, pf, pd in combos:
+            if pd >= 0:
+                env.set_option(_lib.OPT_PDL, pd)
             env.set_option(_lib.OPT_GRAPH_STEPS, g)
             env.set_option(_lib.OPT_VARIANT, variant)
             if pf >= 0:
@@ -66,7 +70,7 @@ def main():
                 env = env.step()
             env.sync(); loop_nodefer = (time.perf_counter() - t0) * 1e3
             fb.Environment.defer = True
-            print(json.dumps({"config": name, "cells": n, "graph_steps": g, "variant": env.info(_lib.INFO_VARIANT), "prefetch": pf, "us_per_step": round(best / steps * 1e3, 2),
+            print(json.dumps({"config": name, "cells": n, "graph_steps": g, "variant": env.info(_lib.INFO_VARIANT), "prefetch": pf, "pdl": pd, "us_per_step": round(best / steps * 1e3, 2),
                               "wall_us_per_step": round(wall / steps * 1e3, 2),
                               "loop_us_per_step": round(loop / steps * 1e3, 2), "loop_no_defer_us_per_step": round(loop_nodefer / steps * 1e3, 2),
                               "MCUPS": round(n * steps / best / 1e3, 1), "finite": bool(np.isfinite(env.cells.rho).all())}), flush=True)
