@@ -353,7 +353,7 @@ struct EngineT final : Engine {
         const int64_t count = plan.NA;
         if (count == 0) return FVDBM_OK;
         NodeArgs<real> a = node_args(count);
-        CU_TRY(launch_k(k_nodes<real, Q>, blocks_for(count * 32, 256), 256, 0, stream, pdl_chain(), a));
+        CU_TRY(launch_k(k_nodes<real, Q>, blocks_for(count * kNodeLanes, 256), 256, 0, stream, pdl_chain(), a));
         ++launches;
         CU_TRY(cudaGetLastError());
         return FVDBM_OK;

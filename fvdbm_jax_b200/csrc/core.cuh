@@ -38,6 +38,7 @@
 namespace fvdbm {
 
 constexpr int kTW = 32;
+constexpr int kNodeLanes = 8;      // lanes cooperating on one boundary node (ring slots j, j+8, ... per lane; xor butterfly over 8)
 constexpr int32_t kHole = INT32_MIN;
 
 // ---- value types ----------------------------------------------------------------------------------
@@ -319,12 +320,13 @@ FVDBM_HD void advance_cell(const Params<real>& P, const GhostTables<real>& G, co
 template <typename real, int Q>
 FVDBM_HD void node_finish(const Params<real>& P, int type, real sw, real srho, real sux, real suy, const real* sneq,
                           real& rho_n, real& ux_n, real& uy_n, real* pdf_n) {
-    if (type == 1) rho_n = v_div(srho, sw);                                  // containers.py:348-351
-    if (type == 2) { ux_n = v_div(sux, sw); uy_n = v_div(suy, sw); }         // containers.py:343-346
+    const real inv = v_div(real(1), sw);        // weighted_avg (utils/utils.py:34-60): one IEEE reciprocal, then products
+    if (type == 1) rho_n = v_mul(srho, inv);                                 // containers.py:348-351
+    if (type == 2) { ux_n = v_mul(sux, inv); uy_n = v_mul(suy, inv); }       // containers.py:343-346
     const Equilibrium<real, Q> E(rho_n, ux_n, uy_n, P);
 #pragma unroll
     for (int q = 0; q < Q; ++q)                                               // containers.py:353-361
-        pdf_n[q] = v_add(E.value(q, P), v_div(sneq[q], sw));
+        pdf_n[q] = v_fma(sneq[q], inv, E.value(q, P));
 }
 
 // contribution of one ring cell to a node's sums

@@ -345,62 +345,58 @@ struct NodeArgs {
 };
 
 template <typename real>
-__device__ __forceinline__ real warp_sum(real v) {
+__device__ __forceinline__ real group_sum(real v) {          // xor butterfly inside an aligned group of kNodeLanes lanes
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = kNodeLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// One active node evaluated by one warp: lanes walk the ring, shfl_xor tree reduction (every lane ends
-// with the same sums), then rho / vel / populations of the node (identical on all lanes).
+// kNodeLanes (8) lanes per active node, four nodes per warp: lane s of a group walks ring slots s, s+8, ... (one
+// ring cell per lane covers the usual vertex valence of 6-8), the 13 partial sums are combined by a 3-level xor
+// butterfly (every lane of the group ends with the same totals), and lane 0 stores rho / vel / populations.
+// (A full warp per node left 24+ lanes idle and spent ~1500 warp-instructions per node: 26 us for the 19.5k
+// boundary nodes of the porous config; profiles/r2_launches_porous.csv.)
 template <typename real, int Q>
-__device__ __forceinline__ void warp_eval_node(const NodeArgs<real>& a, int node, int lane, real& rho_n, real& ux_n, real& uy_n,
-                                               real* pdf_n) {
-    // prescribed values / type are independent of the ring: issue their loads up front so they overlap
-    // the ring gathers instead of adding a dependent memory round trip after the reduction
+__global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
+    const int gtid = (int)(blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+    const int sub = threadIdx.x & (kNodeLanes - 1);
+    const bool valid = gtid / kNodeLanes < a.NA;
+    const int node = valid ? gtid / kNodeLanes : 0;          // idle groups shadow node 0 so that shuffles stay convergent
+    // static data (type, ring table) is independent of the predecessor kernel: issue those loads before the PDL wait
     const int type = a.tn_type[node];
-    rho_n = a.nrho[node]; ux_n = a.nvel[node]; uy_n = a.nvel[a.NTpad + node];
+    const size_t i0 = (size_t)node * a.MR + sub;
+    real w_first = real(0);
+    int32_t c_first = 0;
+    if (sub < a.MR) { w_first = a.ring_w[i0]; c_first = a.ring_cell[i0]; }
+    pdl_wait();                                    // the ring gathers read the populations the previous cell kernel wrote
+    pdl_trigger();
+    real rho_n = a.nrho[node], ux_n = a.nvel[node], uy_n = a.nvel[a.NTpad + node];
     real sw = real(0), srho = real(0), sux = real(0), suy = real(0);
     real sneq[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) sneq[q] = real(0);
-    for (int j = lane; j < a.MR; j += 32) {                 // lane j <-> ring slot j (same order as the CSR)
-        const size_t i = (size_t)node * a.MR + j;
-        const real w = a.ring_w[i];
+    for (int j = sub; j < a.MR; j += kNodeLanes) {          // same slot order per lane as the CSR ring
+        const real w = j == sub ? w_first : a.ring_w[(size_t)node * a.MR + j];
         if (w != real(0)) {
-            const real* p = a.pdf + pdf_index<Q>((int64_t)a.ring_cell[i]);
+            const int32_t c = j == sub ? c_first : a.ring_cell[(size_t)node * a.MR + j];
+            const real* p = a.pdf + pdf_index<Q>((int64_t)c);
             real f[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) f[q] = p[q * kTW];
             node_accumulate<real, Q>(a.P, f, w, sw, srho, sux, suy, sneq);
         }
     }
-    sw = warp_sum(sw); srho = warp_sum(srho); sux = warp_sum(sux); suy = warp_sum(suy);
+    sw = group_sum(sw); srho = group_sum(srho); sux = group_sum(sux); suy = group_sum(suy);
 #pragma unroll
-    for (int q = 0; q < Q; ++q) sneq[q] = warp_sum(sneq[q]);
+    for (int q = 0; q < Q; ++q) sneq[q] = group_sum(sneq[q]);
+    real pdf_n[Q];
     node_finish<real, Q>(a.P, type, sw, srho, sux, suy, sneq, rho_n, ux_n, uy_n, pdf_n);
-}
-
-template <typename real, int Q>
-__device__ __forceinline__ void store_node(const NodeArgs<real>& a, int node, real rho_n, real ux_n, real uy_n, const real* pdf_n) {
-    const int type = a.tn_type[node];
-    if (type == 1) a.nrho[node] = rho_n;
-    if (type == 2) { a.nvel[node] = ux_n; a.nvel[a.NTpad + node] = uy_n; }
+    if (valid && sub == 0) {
+        if (type == 1) a.nrho[node] = rho_n;
+        if (type == 2) { a.nvel[node] = ux_n; a.nvel[a.NTpad + node] = uy_n; }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) a.npdf[q * a.NTpad + node] = pdf_n[q];
-}
-
-template <typename real, int Q>
-__global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
-    const int node = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    pdl_wait();                                    // the ring gathers read the populations the previous cell kernel wrote
-    pdl_trigger();
-    if (node >= a.NA) return;
-    real rho_n, ux_n, uy_n, pdf_n[Q];
-    warp_eval_node<real, Q>(a, node, lane, rho_n, ux_n, uy_n, pdf_n);
-    __syncwarp();
-    if (lane == 0) store_node<real, Q>(a, node, rho_n, ux_n, uy_n, pdf_n);
+        for (int q = 0; q < Q; ++q) a.npdf[q * a.NTpad + node] = pdf_n[q];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

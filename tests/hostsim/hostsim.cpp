@@ -39,13 +39,15 @@ static int run(const fvdbm_desc& d, int nsteps, void* o_pdf, void* o_npdf, void*
     int cur = 0;
     for (int s = 0; s < nsteps; ++s) {
         const real* pin = buf[cur].data();
-        // k_nodes: lane l of the warp accumulates ring slots l, l+32, ...; shfl_xor butterfly (same order as the GPU)
+        // k_nodes: lane l of the node's group accumulates ring slots l, l+8, ...; xor butterfly over the 8 lanes
+        // (same order as the GPU)
+        constexpr int NL = kNodeLanes;
         for (int64_t t = 0; t < pl.NA; ++t) {
-            real sw[32], srho[32], sux[32], suy[32], sneq[32][Q];
-            for (int l = 0; l < 32; ++l) {
+            real sw[NL], srho[NL], sux[NL], suy[NL], sneq[NL][Q];
+            for (int l = 0; l < NL; ++l) {
                 sw[l] = srho[l] = sux[l] = suy[l] = 0;
                 for (int q = 0; q < Q; ++q) sneq[l][q] = 0;
-                for (int64_t j = l; j < pl.MR; j += 32) {
+                for (int64_t j = l; j < pl.MR; j += NL) {
                     const real w = pl.ring_fw[(size_t)t * pl.MR + j];
                     if (!(w != real(0))) continue;
                     real f[Q];
@@ -54,17 +56,17 @@ static int run(const fvdbm_desc& d, int nsteps, void* o_pdf, void* o_npdf, void*
                 }
             }
             auto butterfly = [](real* v) {
-                for (int o = 16; o > 0; o >>= 1) {
-                    real n[32];
-                    for (int l = 0; l < 32; ++l) n[l] = v[l] + v[l ^ o];
-                    for (int l = 0; l < 32; ++l) v[l] = n[l];
+                for (int o = NL / 2; o > 0; o >>= 1) {
+                    real n[NL];
+                    for (int l = 0; l < NL; ++l) n[l] = v[l] + v[l ^ o];
+                    for (int l = 0; l < NL; ++l) v[l] = n[l];
                 }
             };
             butterfly(sw); butterfly(srho); butterfly(sux); butterfly(suy);
             real sq[Q];
             for (int q = 0; q < Q; ++q) {
-                real v[32];
-                for (int l = 0; l < 32; ++l) v[l] = sneq[l][q];
+                real v[NL];
+                for (int l = 0; l < NL; ++l) v[l] = sneq[l][q];
                 butterfly(v);
                 sq[q] = v[0];
             }
