@@ -1007,15 +1007,17 @@ int fvdbm_halo_set_peers(fvdbm_handle* h, const int32_t* sp, const int64_t* sc, 
 // Hilbert-curve key of every cell centroid (same curve as reorder.hilbert_index), OpenMP over cells.
 int fvdbm_sfc_keys(const double* points, const int32_t* elements, int64_t ncells, int K, int bits, double lo_x, double lo_y,
                    double scale, int64_t* keys) {
-    if (!points || !elements || !keys || ncells < 0 || K < 3 || K > 4 || bits < 1 || bits > 30) { g_create_error = "bad argument"; return FVDBM_ERR_ARG; }
+    if (!points || !keys || ncells < 0 || (elements && (K < 3 || K > 4)) || bits < 1 || bits > 30) { g_create_error = "bad argument"; return FVDBM_ERR_ARG; }
     const int64_t n1 = (int64_t(1) << bits) - 1;
     const int nthreads = fvdbm::plan_threads();
     (void)nthreads;
 #pragma omp parallel for num_threads(nthreads) schedule(static)
     for (int64_t c = 0; c < ncells; ++c) {
         double cx = 0, cy = 0;
-        for (int k = 0; k < K; ++k) { cx += points[2 * (int64_t)elements[c * K + k]]; cy += points[2 * (int64_t)elements[c * K + k] + 1]; }
-        cx /= K; cy /= K;
+        if (elements) {
+            for (int k = 0; k < K; ++k) { cx += points[2 * (int64_t)elements[c * K + k]]; cy += points[2 * (int64_t)elements[c * K + k] + 1]; }
+            cx /= K; cy /= K;
+        } else { cx = points[2 * c]; cy = points[2 * c + 1]; }      // points ARE the centroids
         int64_t x = (int64_t)((cx - lo_x) * scale), y = (int64_t)((cy - lo_y) * scale);
         x = x < 0 ? 0 : (x > n1 ? n1 : x); y = y < 0 ? 0 : (y > n1 ? n1 : y);
         int64_t d = 0;

@@ -46,12 +46,22 @@ def hilbert_index(x: np.ndarray, y: np.ndarray, bits: int = 16) -> np.ndarray:
 
 def hilbert_perm(centers: np.ndarray, bits: int = 16) -> np.ndarray:
     """Space-filling-curve ordering from cell centroids (N,2)."""
-    c = np.asarray(centers, dtype=np.float64)
+    c = np.ascontiguousarray(centers, dtype=np.float64)
     lo = c.min(axis=0)
     span = np.maximum(c.max(axis=0) - lo, 1e-300)
     scale = ((1 << bits) - 1) / span.max()
-    g = np.minimum(((c - lo) * scale).astype(np.int64), (1 << bits) - 1)
-    key = hilbert_index(g[:, 0], g[:, 1], bits)
+    key = None
+    if c.shape[0] >= 1 << 16:            # large meshes: native OpenMP helper of the C-ABI library (same curve, same keys)
+        try:
+            from . import _lib
+            key = np.empty(c.shape[0], dtype=np.int64)
+            _lib.check(_lib.load().fvdbm_sfc_keys(c.ctypes.data, None, c.shape[0], 3, bits, float(lo[0]), float(lo[1]), float(scale),
+                                                  key.ctypes.data))
+        except (RuntimeError, OSError):
+            key = None
+    if key is None:
+        g = np.minimum(((c - lo) * scale).astype(np.int64), (1 << bits) - 1)
+        key = hilbert_index(g[:, 0], g[:, 1], bits)
     order = np.argsort(key, kind="stable")
     return order_to_perm(order)
 

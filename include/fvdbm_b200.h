@@ -213,7 +213,8 @@ int  fvdbm_halo_set_peers(fvdbm_handle* h, const int32_t* send_peers, const int6
 
 /* ---- host-only decomposition helper (no GPU needed): Hilbert-curve key of every cell centroid of a raw mesh
  * (points [P*2] f64, elements [ncells*K] i32), centroid -> integer grid by (c - lo) * scale, `bits` per axis;
- * OpenMP over cells (FVDBM_PLAN_THREADS).  Used by partition.sfc_owner_from_raw for 10^8-cell meshes. */
+ * OpenMP over cells (FVDBM_PLAN_THREADS).  elements == NULL: `points` already holds the ncells centroids.
+ * Used by partition.sfc_owner_from_raw (10^8-cell meshes) and by the Hilbert renumbering. */
 int  fvdbm_sfc_keys(const double* points, const int32_t* elements, int64_t ncells, int K, int bits,
                     double lo_x, double lo_y, double scale, int64_t* keys_out);
 
