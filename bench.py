@@ -150,6 +150,24 @@ def porous_raw_and_callbacks(scale, dyn):
     return raw, (lambda m, nodes: meshgen.porous_boundary_conditions(m, nodes)), None
 
 
+def pinned_upload_buffer(shape, tdt, write_combined):
+    """Pinned host buffer the producer only writes and the GPU only reads.  write_combined: cudaHostAlloc with
+    cudaHostAllocWriteCombined (no CPU-cache snooping on the PCIe reads); falls back to torch's pin_memory()."""
+    import torch
+    if write_combined:
+        try:
+            import ctypes as C
+            rt = C.CDLL("libcudart.so.12")
+            ptr = C.c_void_p()
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=tdt).element_size()
+            if rt.cudaHostAlloc(C.byref(ptr), C.c_size_t(nbytes), C.c_uint(0x04)) == 0:      # cudaHostAllocWriteCombined
+                buf = (C.c_char * nbytes).from_address(ptr.value)
+                return torch.frombuffer(buf, dtype=tdt).reshape(shape)
+        except OSError:
+            pass
+    return torch.empty(shape, dtype=tdt).pin_memory()
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this process (and therefore its first-touch pinned buffers) to the CPUs of the GPU's NUMA node."""
     try:
@@ -310,6 +328,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-multi-gpu-check", action="store_true")
+    ap.add_argument("--wc-upload", action="store_true", help="e2e: write-combined pinned memory for the upload buffer")
     ap.add_argument("--ref-nx", type=int, default=0, help="reference arm mesh (0 = same as --nx)")
     ap.add_argument("--ref-inner", type=int, default=10)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -455,7 +474,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         tdt = torch.float32 if real is np.float32 else torch.float64
-        host_pdf = torch.empty((n_local, 9), dtype=tdt).pin_memory()
+        host_pdf = pinned_upload_buffer((n_local, 9), tdt, args.wc_upload)
         rho_out = [torch.empty((n_local, 1), dtype=tdt).pin_memory() for _ in range(2)]
         vel_out = [torch.empty((n_local, 2), dtype=tdt).pin_memory() for _ in range(2)]
         stepper.get_into("cells.pdf", host_pdf.numpy())
@@ -491,7 +510,7 @@ def main():
         e2e = {"value": n_global * inner * reps / dt / 1e6, "unit": "MCUPS",
                "h2d_bytes_per_step": int(host_pdf.numel() * host_pdf.element_size()),
                "d2h_bytes_per_step": int((rho_out[0].numel() + vel_out[0].numel()) * rho_out[0].element_size()),
-               "steps": reps, "numa_node": numa_node,
+               "steps": reps, "numa_node": numa_node, "upload_buffer": "pinned write-combined" if args.wc_upload else "pinned",
                "note": f"per GPU and step: cells.pdf <- pinned host (async upload stream); step({inner}); cells.rho, cells.vel -> "
                        "pinned host (one export pass, async download stream); host reads result k-1 while step k runs; wall clock"}
 

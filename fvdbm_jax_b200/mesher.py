@@ -5,7 +5,7 @@ the notebooks use -- ``import_meshpy``, ``calc_mesh_properties``, ``to_env``, ``
 ``set_rho_node``, ``to_vtk``, ``to_pickle``/``from_pickle`` -- but replaces its per-element Python
 loops (~130 us/cell) by sort-based NumPy so 10^7-cell meshes are reachable.
 
-Contract (tests/test_mesher_parity.py): every integer array (``cells`` after the CCW fix, ``faces``
+Contract (tests/test_host_logic.py::test_mesher_matches_reference_mesher): every integer array (``cells`` after the CCW fix, ``faces``
 after the boundary flip, ``cell_face_indices``, ``cell_face_normal_signs``, ``face_cell_indices``,
 ``point_cell_indices``) is bit-identical to the reference Mesher's; float geometry agrees to a few
 ulp (the reference's 2-vector ``np.dot``/``np.linalg.norm`` go through BLAS ddot whose FMA use is

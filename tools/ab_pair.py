@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--scheme", default="lax_wendroff")
     ap.add_argument("--sustained", type=int, default=2000)
     ap.add_argument("--reorder", default="hilbert")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--tag", default=os.path.basename(os.environ.get("FVDBM_LIB", "default")))
     args = ap.parse_args()
     cache = f"/tmp/fvdbm_problem_{args.nx}_{args.scheme}.pkl"
@@ -29,10 +30,10 @@ def main():
         m, dyn, cells, faces, nodes, _ = bench.build_problem(args.nx, args.nx, args.scheme)
         pickle.dump((cells, faces, nodes), open(cache, "wb"), protocol=4)
     n = cells.face_indices.shape[0]
-    per_cell, per_face = bench.B_ALG[("f32", args.scheme)]
+    per_cell, per_face = bench.B_ALG[(args.dtype, args.scheme)]
     b_alg = per_cell + per_face * faces.n.shape[0] / n
     peak, _ = bench.measured_peak()
-    env = fb.Environment(cells, faces, nodes, dtype=np.float32, reorder=args.reorder)
+    env = fb.Environment(cells, faces, nodes, dtype=np.float32 if args.dtype == "f32" else np.float64, reorder=args.reorder)
     env.init(); env.build()
     for variant in [int(v) for v in args.variants.split(",")]:
         for dist in [int(d) for d in args.dists.split(",")]:
@@ -42,7 +43,7 @@ def main():
             env.step(500)
             sus = env.step_timed(args.sustained) / args.sustained
             f = lambda ms: round(n * b_alg / (ms * 1e-3) / 1e9 / peak, 4)
-            print(json.dumps({"lib": args.tag, "reorder": args.reorder, "variant": variant, "prefetch_dist": dist, "burst_ms": round(burst, 4),
+            print(json.dumps({"lib": args.tag, "dtype": args.dtype, "scheme": args.scheme, "reorder": args.reorder, "variant": variant, "prefetch_dist": dist, "burst_ms": round(burst, 4),
                               "sustained_ms": round(sus, 4), "burst_frac": f(burst), "sustained_frac": f(sus),
                               "sustained_MCUPS": round(n / sus / 1e3, 1)}), flush=True)
             time.sleep(1.0)
