@@ -41,9 +41,8 @@ env = Environment(cells, faces, nodes)                         # notebook c16
 env.init()
 env.build()                                                    # engine creation (context, upload) outside the timing
 t0 = time.time()
-chunk = 1000
-for i in range(args.steps // chunk):                           # notebook c17: for i in tqdm(range(100000)): env = env.step()
-    env = env.step(chunk)
+for i in range(args.steps):                                    # notebook c17, verbatim: single steps are batched by the
+    env = env.step()                                           # engine (flushed every 50 steps / before any read)
 env.sync()
 dt_wall = time.time() - t0
 vel, dens = env.cells.vel, env.cells.rho                       # notebook c18-c20

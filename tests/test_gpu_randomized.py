@@ -9,7 +9,7 @@ import golden
 pytestmark = pytest.mark.gpu
 
 fb = pytest.importorskip("fvdbm_jax_b200")
-from fvdbm_jax_b200 import meshgen  # noqa: E402
+from fvdbm_jax_b200 import _lib, meshgen  # noqa: E402
 from oracle.step_numpy import StepOracle  # noqa: E402
 
 
@@ -63,6 +63,8 @@ def test_random_problem_matches_oracle(seed):
             pytest.skip("random boundary conditions drove this case unstable (rounding differences are amplified)")
         with fb.Environment(cells, faces, nodes, dtype=dtype, reorder="hilbert" if seed % 2 else "rcm") as env:
             env.init()
+            if dtype is np.float32 and seed % 3 != 2:       # small meshes default to the thread-per-cell kernel: force the
+                env.set_option(_lib.OPT_VARIANT, _lib.VARIANT_PAIR)      # packed two-cells-per-thread kernel on 2 of 3 seeds
             env = env.step(steps)
             exp = o.state()
             for name in golden.STATE:
