@@ -84,12 +84,12 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         out, _ = self.proc.communicate(timeout=10)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             p = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
             except (ValueError, IndexError):
                 continue
             for name, val in zip(names, p[3:7]):
@@ -97,7 +97,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None}
 
 
 def measured_peak():

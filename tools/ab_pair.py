@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--dists", default="0")
     ap.add_argument("--variants", default="3")
     ap.add_argument("--scheme", default="lax_wendroff")
-    ap.add_argument("--sustained", type=int, default=2000)
+    ap.add_argument("--sustained", type=int, default=4000)
     ap.add_argument("--reorder", default="hilbert")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--tag", default=os.path.basename(os.environ.get("FVDBM_LIB", "default")))
@@ -41,11 +41,14 @@ def main():
             env.step(20); env.sync()
             burst = min(env.step_timed(50) for _ in range(3)) / 50
             env.step(500)
+            sampler = bench.ClockSampler(0)
             sus = env.step_timed(args.sustained) / args.sustained
+            clk = sampler.stop()
             f = lambda ms: round(n * b_alg / (ms * 1e-3) / 1e9 / peak, 4)
             print(json.dumps({"lib": args.tag, "dtype": args.dtype, "scheme": args.scheme, "reorder": args.reorder, "variant": variant, "prefetch_dist": dist, "burst_ms": round(burst, 4),
                               "sustained_ms": round(sus, 4), "burst_frac": f(burst), "sustained_frac": f(sus),
-                              "sustained_MCUPS": round(n / sus / 1e3, 1)}), flush=True)
+                              "sustained_MCUPS": round(n / sus / 1e3, 1), "sm_mhz": clk.get("sm_mhz"), "power_w": clk.get("power_w"),
+                              "reasons": clk.get("reasons")}), flush=True)
             time.sleep(1.0)
     env.close()
 
