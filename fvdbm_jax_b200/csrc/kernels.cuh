@@ -167,18 +167,8 @@ __global__ void __launch_bounds__(FVDBM_PAIR_THREADS, FVDBM_PAIR_MINCTAS) k_fuse
         float fx[Q], fy[Q];
         float2 fn[Q];
         if (code[k].x >= 0 && code[k].y >= 0) {     // both sides interior (all but the O(sqrt N) border cells)
-            // The face shared by the thread's own two cells needs no gather: the partner's populations are already in
-            // this thread's registers (same bits the gather would return).  The planner numbers cells in face-adjacent
-            // pairs (plan.hpp), so about one side in three of every cell is served this way.
-            const int64_t nx = (int64_t)(code[k].x >> 2), ny = (int64_t)(code[k].y >> 2);
-            if (nx == c + 1) {
-#pragma unroll
-                for (int q = 1; q < Q; ++q) fx[q] = f[q].y;
-            } else gather(nx, fx);
-            if (ny == c) {
-#pragma unroll
-                for (int q = 1; q < Q; ++q) fy[q] = f[q].x;
-            } else gather(ny, fy);
+            gather((int64_t)(code[k].x >> 2), fx);
+            gather((int64_t)(code[k].y >> 2), fy);
         } else {
             float f0[Q], f1[Q];
 #pragma unroll

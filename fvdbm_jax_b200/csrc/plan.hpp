@@ -177,36 +177,9 @@ struct Plan {
                     const int32_t o = other[c * K + k];
                     if (o == -1 || o >= No) border[c] = 1;
                 }
-            // Within each group cells are laid out in locality order as face-adjacent PAIRS on (even, odd) positions:
-            // the two-cells-per-thread kernel then finds one neighbour of each cell in its own registers.  Greedy
-            // matching along the order: a cell takes its not-yet-placed face neighbour of the same group that comes
-            // next in the order; cells without one are paired with the next such cell (no shared face, plain gathers).
-            std::vector<int32_t> rank_of(N);
-            for (int64_t r = 0; r < N; ++r) rank_of[order[r]] = (int32_t)r;
-            std::vector<uint8_t> placed(N, 0);
-            auto lay_out = [&](uint8_t grp) {
-                int32_t single = -1;
-                for (int64_t r = 0; r < No; ++r) {
-                    const int32_t c = order[r];
-                    if (border[c] != grp || placed[c]) continue;
-                    int32_t best = -1;
-                    for (int k = 0; k < K; ++k) {
-                        const int32_t o = other[(int64_t)c * K + k];
-                        if (o < 0 || o >= No || o == c || placed[o] || border[o] != grp) continue;
-                        if (best < 0 || rank_of[o] < rank_of[best]) best = o;
-                    }
-                    placed[c] = 1;
-                    if (best >= 0) {
-                        placed[best] = 1;
-                        pos[c] = (int32_t)p++; pos[best] = (int32_t)p++;
-                    } else if (single < 0) single = c;
-                    else { pos[single] = (int32_t)p++; pos[c] = (int32_t)p++; single = -1; }
-                }
-                if (single >= 0) { pos[single] = (int32_t)p++; ++p; }     // odd one out: its partner position stays a hole
-            };
-            lay_out(0);
+            for (int64_t r = 0; r < No; ++r) if (!border[order[r]]) pos[order[r]] = (int32_t)p++;
             Bstart = round_up(p, PAD_TO); p = Bstart;
-            lay_out(1);
+            for (int64_t r = 0; r < No; ++r) if (border[order[r]]) pos[order[r]] = (int32_t)p++;
             Oend = p; Hstart = round_up(p, PAD_TO); p = Hstart;
             for (int64_t r = No; r < N; ++r) pos[order[r]] = (int32_t)p++;
         } else {
@@ -320,8 +293,7 @@ struct Plan {
             for (int64_t pc = Bstart; pc < Oend; ++pc) {
                 const int64_t c = ipos[pc];
                 int nb = 0;
-                if (c >= 0)                                      // (a hole can sit inside the group: odd one out of the pairing)
-                    for (int k = 0; k < K; ++k) nb += other[c * K + k] == -1;
+                for (int k = 0; k < K; ++k) nb += other[c * K + k] == -1;
                 bside_base[pc - Bstart + 1] = bside_base[pc - Bstart] + nb;
             }
             NB = bside_base[std::max<int64_t>(Oend - Bstart, 0)];
