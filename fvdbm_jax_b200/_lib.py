@@ -19,7 +19,7 @@ COMM_ID_BYTES = 128
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 SCHEME_UPWIND, SCHEME_LAX_WENDROFF = 0, 1
 MODE_AUTO, MODE_STAGED, MODE_FUSED = 0, 1, 2
-VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA, VARIANT_PAIR = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA, VARIANT_PAIR, VARIANT_REC = 0, 1, 2, 3, 4
 (CELL_PDF, CELL_RHO, CELL_VEL, CELL_PDF_EQ, FACE_FLUX, NODE_PDF, NODE_RHO, NODE_VEL,
  CELL_PDF_PREV) = range(9)
 (INFO_MODE, INFO_STEPS, INFO_LAUNCHES, INFO_TRACKED_NODES, INFO_BOUNDARY_SIDES, INFO_DEVICE_BYTES,

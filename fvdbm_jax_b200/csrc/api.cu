@@ -147,6 +147,7 @@ struct EngineT final : Engine {
     int variant = FVDBM_VARIANT_DIRECT;   // fp32: PAIR (two cells per thread, packed math); fp64: DIRECT; TMA is opt-in
     int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
     int pdl = 0;                         // programmatic dependent launch chain (default: on below 1M cells)
+    int lay = 0;                         // population layout of pdf[0..1] (core.cuh: 0 tiled AoSoA, 1 records); follows the variant
     int prefetch_dist = 296;             // CTAs of L2 look-ahead (0.4 of a resident wave); measured on B200: burst 0.231 -> 0.194 ms per
                                          // 10M-cell iteration, sustained +2-3 % (profiles/r2_ab_pair_kernel.jsonl)
     int num_sms = 148;
@@ -317,7 +318,9 @@ struct EngineT final : Engine {
     size_t stage_bytes(int tc) const { return tma_stage_bytes<real, Q, K, SCHEME>(tc); }
 
     int sanitize_options() {
-        if (variant != FVDBM_VARIANT_DIRECT && variant != FVDBM_VARIANT_TMA && variant != FVDBM_VARIANT_PAIR) { err = "unknown variant"; return FVDBM_ERR_ARG; }
+        if (variant != FVDBM_VARIANT_DIRECT && variant != FVDBM_VARIANT_TMA && variant != FVDBM_VARIANT_PAIR && variant != FVDBM_VARIANT_REC) { err = "unknown variant"; return FVDBM_ERR_ARG; }
+        if (variant == FVDBM_VARIANT_REC && !rec_available()) { err = "the record-layout kernel exists for fp32 D2Q9 only"; return FVDBM_ERR_ARG; }
+        if (variant == FVDBM_VARIANT_REC && mode != FVDBM_MODE_FUSED) { err = "the record-layout kernel needs the fused mode"; return FVDBM_ERR_ARG; }
         if (variant == FVDBM_VARIANT_PAIR && sizeof(real) != 4) { err = "the packed two-cells-per-thread kernel exists for fp32 only"; return FVDBM_ERR_ARG; }
         if (tile_cells != 128 && tile_cells != 256 && tile_cells != 512) { err = "tile_cells must be 128, 256 or 512"; return FVDBM_ERR_ARG; }
         if (stages < 2 || stages > 8) { err = "stages must be in 2..8"; return FVDBM_ERR_ARG; }
@@ -325,7 +328,7 @@ struct EngineT final : Engine {
         while (tile_cells > 128 && kTmaHeader + stages * stage_bytes(tile_cells) > max_smem) tile_cells /= 2;
         if (graph_steps < 0) graph_steps = 0;
         if (graph_steps & 1) ++graph_steps;
-        return FVDBM_OK;
+        return set_layout(variant == FVDBM_VARIANT_REC ? 1 : 0);
     }
 
     // ---------------------------------------------------------------- launches
@@ -344,7 +347,7 @@ struct EngineT final : Engine {
 
     NodeArgs<real> node_args(int64_t count) const {
         NodeArgs<real> a;
-        a.P = P; a.pdf = pdf[cur].p;
+        a.P = P; a.pdf = pdf[cur].p; a.lay = lay; a.Npad = plan.Npad;
         a.ring_cell = ring_cell.p; a.ring_w = ring_w.p; a.MR = (int)plan.MR; a.tn_type = tn_type.p;
         a.npdf = npdf.p; a.nrho = nrho.p; a.nvel = nvel.p; a.NTpad = plan.NTpad; a.NA = (int)count;
         return a;
@@ -362,7 +365,9 @@ struct EngineT final : Engine {
     int launch_fused(int64_t begin, int64_t end, cudaStream_t st) {
         if (end <= begin) return FVDBM_OK;
         FusedArgs<real> a = fused_args(begin, end);
-        if (variant == FVDBM_VARIANT_PAIR) {
+        if (variant == FVDBM_VARIANT_REC) {
+            launch_rec(a, end - begin, st);
+        } else if (variant == FVDBM_VARIANT_PAIR) {
             launch_pair(a, end - begin, st);
         } else if (variant == FVDBM_VARIANT_DIRECT) {
             CU_TRY(launch_k(k_fused_direct<real, Q, K, SCHEME>, blocks_for(end - begin, 256), 256, 0, st, pdl_chain(), a));
@@ -391,6 +396,28 @@ struct EngineT final : Engine {
         launch_k(k_fused_pair<Q, K, SCHEME>, blocks_for(cells / 2, FVDBM_PAIR_THREADS), FVDBM_PAIR_THREADS, 0, st, pdl_chain(), a);
     }
     void launch_pair(const FusedArgs<double>&, int64_t, cudaStream_t) {}
+    // fp32 D2Q9 only: thread per cell over the record layout
+    void launch_rec(const FusedArgs<float>& a, int64_t cells, cudaStream_t st) {
+        if constexpr (Q == 9) launch_k(k_fused_rec<K, SCHEME>, blocks_for(cells, 256), 256, 0, st, pdl_chain(), a, plan.Npad);
+    }
+    void launch_rec(const FusedArgs<double>&, int64_t, cudaStream_t) {}
+    static constexpr bool rec_available() { return sizeof(real) == 4 && Q == 9; }
+
+    // the population buffers follow the variant's layout; switching re-lays both out (rare: set_option only)
+    int set_layout(int want) {
+        if (want == lay || !pdf[0].p) { lay = want; return FVDBM_OK; }
+        DevBuf<real> tmp;
+        CU_TRY(tmp.alloc(pdf[0].n));
+        for (int b = 0; b < 2; ++b) {
+            k_relayout<real, Q><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(pdf[b].p, lay, tmp.p, want, plan.Npad);
+            ++launches;
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(pdf[b].p, tmp.p, pdf[b].bytes(), cudaMemcpyDeviceToDevice, stream));
+        }
+        CU_TRY(cudaStreamSynchronize(stream));
+        lay = want;
+        return FVDBM_OK;
+    }
 
     int ensure_staged_buffers() {
         if (s_flux.p) return FVDBM_OK;
@@ -404,7 +431,7 @@ struct EngineT final : Engine {
 
     int launch_faces(const real* src_pdf) {
         FaceArgs<real> a;
-        a.P = P; a.pdf = src_pdf; a.fcell = s_fcell.p; a.fnode = s_fnode.p; a.fdist = s_fdist.p; a.fn = s_fn.p;
+        a.P = P; a.pdf = src_pdf; a.lay = lay; a.Npad = plan.Npad; a.fcell = s_fcell.p; a.fnode = s_fnode.p; a.fdist = s_fdist.p; a.fn = s_fn.p;
         a.fL = s_fL.p; a.npdf = npdf.p; a.NTpad = plan.NTpad; a.F = plan.F;
         a.last_pos = plan.pos[plan.N - 1]; a.flux = s_flux.p;
         k_s_faces<real, Q, SCHEME><<<blocks_for(plan.F, 256), 256, 0, stream>>>(a);
@@ -416,12 +443,12 @@ struct EngineT final : Engine {
     int step_staged_once() {
         int rc = ensure_staged_buffers();
         if (rc) return rc;
-        k_s_moments<real, Q><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, pdf[cur].p, ipos.p, plan.Npad, s_rho.p,
+        k_s_moments<real, Q><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, pdf[cur].p, lay, ipos.p, plan.Npad, s_rho.p,
                                                                              s_ux.p, s_uy.p, s_feq.p);
         ++launches;
         if ((rc = launch_nodes())) return rc;
         if ((rc = launch_faces(pdf[cur].p))) return rc;
-        k_s_cells<real, Q, K><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, pdf[cur].p, s_feq.p, s_flux.p, s_cface.p,
+        k_s_cells<real, Q, K><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(P, lay, pdf[cur].p, s_feq.p, s_flux.p, s_cface.p,
                                                                             s_csign.p, ipos.p, plan.Npad, plan.No, s_inv_area.p, pdf[nxt()].p);
         ++launches;
         CU_TRY(cudaGetLastError());
@@ -679,9 +706,9 @@ struct EngineT final : Engine {
             if ((rc = claim_outbox(o, (size_t)N * Q))) return rc;
             o.moments_steps = -1;
             if (field == FVDBM_CELL_PDF_EQ)
-                k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(P, pdf[prev].p, pos.p, rows, nullptr, nullptr, o.buf.p);
+                k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(P, pdf[prev].p, lay, plan.Npad, pos.p, rows, nullptr, nullptr, o.buf.p);
             else
-                k_export_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[field == FVDBM_CELL_PDF ? cur : prev].p, pos.p, rows, o.buf.p);
+                k_export_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[field == FVDBM_CELL_PDF ? cur : prev].p, lay, plan.Npad, pos.p, rows, o.buf.p);
             ++launches;
             CU_TRY(cudaGetLastError());
             return ship(o, o.buf.p, dst, bytes, ticket);
@@ -696,7 +723,7 @@ struct EngineT final : Engine {
             if (!o) {
                 o = &outbox[tickets & 1];
                 if ((rc = claim_outbox(*o, (size_t)N * 3))) return rc;
-                k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(P, pdf[prev].p, pos.p, rows, o->buf.p, o->buf.p + rows, nullptr);
+                k_export_moments<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(P, pdf[prev].p, lay, plan.Npad, pos.p, rows, o->buf.p, o->buf.p + rows, nullptr);
                 ++launches;
                 CU_TRY(cudaGetLastError());
                 o->moments_steps = steps; o->moments_rows = rows;
@@ -755,7 +782,7 @@ struct EngineT final : Engine {
             CU_TRY(cudaMemcpyAsync(inbox.p, src, bytes, cudaMemcpyHostToDevice, xin));
             CU_TRY(cudaEventRecord(inbox_filled, xin));
             CU_TRY(cudaStreamWaitEvent(stream, inbox_filled, 0));
-            k_import_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[cur].p, pos.p, rows, inbox.p);
+            k_import_cells<real, Q><<<blocks_for(rows, 256), 256, 0, stream>>>(pdf[cur].p, lay, plan.Npad, pos.p, rows, inbox.p);
             ++launches;
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaEventRecord(inbox_consumed, stream));
@@ -787,7 +814,7 @@ struct EngineT final : Engine {
         if (!bad) { err = "null argument"; return FVDBM_ERR_ARG; }
         if (!counter.p) CU_TRY(counter.alloc(1));
         CU_TRY(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), stream));
-        k_count_nonfinite<real, Q><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(pdf[cur].p, ipos.p, plan.Npad, plan.No, counter.p);
+        k_count_nonfinite<real, Q><<<blocks_for(plan.Npad, 256), 256, 0, stream>>>(pdf[cur].p, lay, ipos.p, plan.Npad, plan.No, counter.p);
         ++launches;
         CU_TRY(cudaGetLastError());
         unsigned long long host = 0;
@@ -875,7 +902,7 @@ struct EngineT final : Engine {
     int halo_pack(void* buf) override {
         CU_TRY(cudaSetDevice(device));
         if (halo_send.n == 0) return FVDBM_OK;
-        k_pack<real, Q><<<blocks_for((int64_t)halo_send.n * Q, 256), 256, 0, stream>>>(pdf[cur].p, halo_send.p, (int64_t)halo_send.n,
+        k_pack<real, Q><<<blocks_for((int64_t)halo_send.n * Q, 256), 256, 0, stream>>>(pdf[cur].p, lay, plan.Npad, halo_send.p, (int64_t)halo_send.n,
                                                                                    static_cast<real*>(buf));
         ++launches;
         CU_TRY(cudaGetLastError());
@@ -884,7 +911,7 @@ struct EngineT final : Engine {
     int halo_unpack(const void* buf) override {
         CU_TRY(cudaSetDevice(device));
         if (halo_recv.n == 0) return FVDBM_OK;
-        k_unpack<real, Q><<<blocks_for((int64_t)halo_recv.n * Q, 256), 256, 0, stream>>>(pdf[cur].p, halo_recv.p, (int64_t)halo_recv.n,
+        k_unpack<real, Q><<<blocks_for((int64_t)halo_recv.n * Q, 256), 256, 0, stream>>>(pdf[cur].p, lay, plan.Npad, halo_recv.p, (int64_t)halo_recv.n,
                                                                                      static_cast<const real*>(buf));
         ++launches;
         CU_TRY(cudaGetLastError());

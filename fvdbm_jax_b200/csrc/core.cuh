@@ -149,6 +149,18 @@ FVDBM_HD size_t pdf_index(int64_t cell) {       // index of population 0; popula
     return (size_t)(cell >> 5) * (size_t)(Q * kTW) + (size_t)(cell & 31);
 }
 
+// Two population layouts (chosen per handle, api.cu):
+//   lay 0  tiled AoSoA (above): every population streams coalesced; a neighbour's Q-1 moving populations lie in Q-1
+//          different 32-byte sectors.
+//   lay 1  records: the Q-1 MOVING populations of a cell are contiguous ((Q-1)*sizeof(real) bytes: exactly one sector
+//          for D2Q9 fp32), the rest population q = 0 -- never gathered, KSI_0 = 0 -- lives in a separate array behind
+//          the records.  A neighbour gather is two 128-bit loads from one sector.
+template <int Q>
+FVDBM_HD size_t pdf_off(int lay, int64_t Npad, int64_t cell, int q) {
+    return lay == 0 ? pdf_index<Q>(cell) + (size_t)q * kTW
+                    : (q == 0 ? (size_t)Npad * (Q - 1) + (size_t)cell : (size_t)cell * (Q - 1) + (size_t)(q - 1));
+}
+
 // KSI_q . (x, y) given s = x + y and d = x - y (each rounded once); negations and doubling are exact
 template <typename V>
 FVDBM_HD V ksi_dot(int q, V x, V y, V s, V d) {

@@ -201,6 +201,129 @@ __global__ void __launch_bounds__(FVDBM_PAIR_THREADS, FVDBM_PAIR_MINCTAS) k_fuse
 }
 
 // ------------------------------------------------------------------------------------------------
+// V4 (fp32, D2Q9): thread per cell over the RECORD layout (core.cuh: lay 1).  The eight moving populations of a
+// cell are one 32-byte sector, so a neighbour gather is two LDG.E.128 from ONE sector (the AoSoA kernels touch
+// eight sectors with eight LDG.E.32), the own populations are two LDG.E.128 + one LDG.E.32, the result two
+// STG.E.128 + one STG.E.32; and the arithmetic is packed over POPULATION pairs (q1,q2) (q3,q4) (q5,q6) (q7,q8):
+// per side the four distinct KSI.M values form two pairs W0 = (Mx, My), W2 = (Mx+My, My-Mx) and their negations,
+// so c = A - W Gd, f* = f_slot0 + (fn - f) c and fl += f* W are four FFMA2 each, with scalar side coefficients as
+// broadcast operands.  Same canonical operation sequence per (cell, population) as every other kernel -> same bits.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
+
+template <int K, int SCHEME>
+__global__ void __launch_bounds__(256, 3) k_fused_rec(const FusedArgs<float> a, const int64_t Npad) {
+    constexpr int Q = 9, NC = SCHEME == 0 ? 2 : 4;
+    const int64_t nblk = gridDim.x;
+    const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
+    const int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
+    const float* rest_in = a.pdf_in + (size_t)Npad * (Q - 1);
+    if (a.prefetch_dist > 0 && threadIdx.x == 0) {
+        const int64_t first = a.cell_begin + (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x;
+        if (first >= a.cell_begin && first + blockDim.x <= a.cell_end) {
+            const size_t mt = (size_t)(first >> 5);
+            prefetch_l2_bulk(a.pdf_in + (size_t)first * (Q - 1), (uint32_t)(blockDim.x * (Q - 1) * sizeof(float)));
+            prefetch_l2_bulk(rest_in + first, (uint32_t)(blockDim.x * sizeof(float)));
+            prefetch_l2_bulk(a.ccoef + mt * (K * NC * kTW), (uint32_t)(blockDim.x * K * NC * sizeof(float)));
+            prefetch_l2_bulk(a.ccode + mt * (K * kTW), (uint32_t)(blockDim.x * K * sizeof(int32_t)));
+        }
+    }
+    if (c >= a.cell_end) return;
+    const size_t tile = (size_t)(c >> 5);
+    const int lane = (int)(c & 31);
+    const int32_t* gc = a.ccode + tile * (K * kTW) + lane;
+    int32_t code[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) code[k] = __ldg(gc + k * kTW);
+    float coef[K * NC];
+    const float* gco = a.ccoef + tile * (K * NC * kTW) + lane;
+#pragma unroll
+    for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
+    const float4* rec = reinterpret_cast<const float4*>(a.pdf_in) + 2 * c;
+    const float4 ra = __ldg(rec), rb = __ldg(rec + 1);
+    const float f0 = __ldg(rest_in + c);
+    const float2 f[4] = {f2(ra.x, ra.y), f2(ra.z, ra.w), f2(rb.x, rb.y), f2(rb.z, rb.w)};     // (q1,q2) (q3,q4) (q5,q6) (q7,q8)
+    const bool live = code[0] != kHole;
+    if (!live) code[0] = 0;                        // neutral: interior side towards position 0
+    pdl_wait();
+    pdl_trigger();
+    float2 fl[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int32_t cd = code[k];
+        float2 fn[4];
+        if (cd >= 0) {
+            const float4* rn = reinterpret_cast<const float4*>(a.pdf_in) + 2 * (int64_t)(cd >> 2);
+            const float4 na = __ldg(rn), nb = __ldg(rn + 1);
+            fn[0] = f2(na.x, na.y); fn[1] = f2(na.z, na.w); fn[2] = f2(nb.x, nb.y); fn[3] = f2(nb.z, nb.w);
+        } else {                                    // ghost side (border cells only): scalar path of core.cuh
+            const float fo[Q] = {f0, f[0].x, f[0].y, f[1].x, f[1].y, f[2].x, f[2].y, f[3].x, f[3].y};
+            float g[Q];
+            far_populations<float, Q>(a.G, cd, fo, [](int64_t, float*) {}, g);
+            fn[0] = f2(g[1], g[2]); fn[1] = f2(g[3], g[4]); fn[2] = f2(g[5], g[6]); fn[3] = f2(g[7], g[8]);
+        }
+        const bool slot1 = code_slot(cd) != 0, neg = code_neg(cd) != 0;
+        const float Mx = coef[k * NC + 0], My = coef[k * NC + 1];
+        const float Ms = v_add(Mx, My), Md = v_sub(Mx, My), nMd = v_sub(My, Mx);     // nMd == -Md exactly
+        const float2 W0 = f2(Mx, My), W2 = f2(Ms, nMd);
+        const float2 W[4] = {W0, v_neg(W0), W2, v_neg(W2)};                          // KSI_q . M for q = 1..8
+        if (SCHEME == 0) {
+            // varpi_q >= 0 <=> sigma W_q >= 0; the own cell is upstream iff (slot == 0) == (varpi_q >= 0)   (core.cuh)
+            const bool gx = neg ? Mx <= 0.f : Mx >= 0.f, lx = neg ? Mx >= 0.f : Mx <= 0.f;
+            const bool gy = neg ? My <= 0.f : My >= 0.f, ly = neg ? My >= 0.f : My <= 0.f;
+            const bool gs = neg ? Ms <= 0.f : Ms >= 0.f, ls = neg ? Ms >= 0.f : Ms <= 0.f;
+            const bool gd = neg ? Md <= 0.f : Md >= 0.f, ld = neg ? Md >= 0.f : Md <= 0.f;
+            const bool2 ge[4] = {bool2{gx, gy}, bool2{lx, ly}, bool2{gs, ld}, bool2{ls, gd}};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 fs = v_sel(bool2{ge[j].x == slot1, ge[j].y == slot1}, fn[j], f[j]);
+                fl[j] = v_fma(fs, W[j], fl[j]);
+            }
+        } else {
+            const float A = coef[k * NC + 2], Gd = v_mul(a.P.dt, coef[k * NC + 3]);
+            const float2 nGd = v_bcast<float2>(-Gd), A2 = v_bcast<float2>(A);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 cj = v_fma(W[j], nGd, A2);
+                const float2 fs = v_fma(v_sub(fn[j], f[j]), cj, slot1 ? fn[j] : f[j]);
+                fl[j] = v_fma(fs, W[j], fl[j]);
+            }
+        }
+    }
+    // moments, equilibrium, relaxation: the scalar canonical order for the sums, packed pairs for the rest
+    float r = f0;
+    r = v_add(r, f[0].x); r = v_add(r, f[0].y); r = v_add(r, f[1].x); r = v_add(r, f[1].y);
+    r = v_add(r, f[2].x); r = v_add(r, f[2].y); r = v_add(r, f[3].x); r = v_add(r, f[3].y);
+    float jx = f[0].x, jy = f[0].y;                                   // q1, q2
+    jx = v_sub(jx, f[1].x); jx = v_add(jx, f[2].x); jx = v_sub(jx, f[2].y); jx = v_sub(jx, f[3].x); jx = v_add(jx, f[3].y);
+    jy = v_sub(jy, f[1].y); jy = v_add(jy, f[2].x); jy = v_add(jy, f[2].y); jy = v_sub(jy, f[3].x); jy = v_sub(jy, f[3].y);
+    const float ux = v_div(jx, r), uy = v_div(jy, r);
+    const float uu = v_fma(ux, ux, v_mul(uy, uy));
+    const float us = v_add(ux, uy), nud = v_sub(uy, ux);               // nud == -(ux - uy) exactly
+    const float base = v_fma(-uu, a.P.inv_2cs2, 1.0f);
+    const float2 ku0 = f2(ux, uy), ku2 = f2(us, nud);
+    const float2 ku[4] = {ku0, v_neg(ku0), ku2, v_neg(ku2)};
+    const float2 b2 = v_bcast<float2>(a.P.inv_2cs4), a2 = v_bcast<float2>(a.P.inv_cs2), base2 = v_bcast<float2>(base);
+    const float wr0 = v_mul(a.P.w[0], r), wr1 = v_mul(a.P.w[1], r), wr5 = v_mul(a.P.w[5], r);
+    const float2 dt2 = v_bcast<float2>(a.P.dt), it2 = v_bcast<float2>(a.P.inv_tau);
+    float2 out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 poly = v_fma(ku[j], v_fma(ku[j], b2, a2), base2);
+        const float2 g = v_fma(v_bcast<float2>(j < 2 ? wr1 : wr5), poly, v_neg(f[j]));
+        out[j] = v_fma(dt2, v_fma(it2, g, v_neg(fl[j])), f[j]);
+    }
+    const float g0 = v_fma(wr0, base, -f0);                            // poly_0 == base exactly (KSI_0 = 0)
+    const float out0 = v_fma(a.P.dt, v_fma(a.P.inv_tau, g0, -0.0f), f0);
+    if (live) {
+        float4* ro = reinterpret_cast<float4*>(a.pdf_out) + 2 * c;
+        ro[0] = make_float4(out[0].x, out[0].y, out[1].x, out[1].y);
+        ro[1] = make_float4(out[2].x, out[2].y, out[3].x, out[3].y);
+        a.pdf_out[(size_t)Npad * (Q - 1) + c] = out0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // V2: persistent CTAs; each CTA walks tiles of blockDim.x cells.  Thread 0 keeps `stages-1` tiles
 // in flight with cp.async.bulk (TMA bulk copies: populations, side codes, side coefficients are
 // each one contiguous block thanks to the AoSoA layout) completing on per-stage mbarriers.
@@ -332,7 +455,8 @@ __global__ void __launch_bounds__(512) k_fused_tma(const FusedArgs<real> a, cons
 template <typename real>
 struct NodeArgs {
     Params<real> P;
-    const real* __restrict__ pdf;          // current populations (AoSoA)
+    const real* __restrict__ pdf;          // current populations
+    int lay; int64_t Npad;                 // their layout (core.cuh: pdf_off)
     const int32_t* __restrict__ ring_cell;  // fixed-width ring table [NA][MR] (plan.hpp: ring_fcell)
     const real* __restrict__ ring_w;        //                               (ring_fw; 0 = unused slot)
     int MR;
@@ -379,10 +503,9 @@ __global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
         const real w = j == sub ? w_first : a.ring_w[(size_t)node * a.MR + j];
         if (w != real(0)) {
             const int32_t c = j == sub ? c_first : a.ring_cell[(size_t)node * a.MR + j];
-            const real* p = a.pdf + pdf_index<Q>((int64_t)c);
             real f[Q];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) f[q] = p[q * kTW];
+            for (int q = 0; q < Q; ++q) f[q] = a.pdf[pdf_off<Q>(a.lay, a.Npad, (int64_t)c, q)];
             node_accumulate<real, Q>(a.P, f, w, sw, srho, sux, suy, sneq);
         }
     }
@@ -403,29 +526,28 @@ __global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
 // staged path: S1+S2, S4, S5 as separate kernels over the reference's data model.
 // ------------------------------------------------------------------------------------------------
 template <typename real, int Q>
-__global__ void __launch_bounds__(256) k_s_moments(const Params<real> P, const real* __restrict__ pdf,
+__global__ void __launch_bounds__(256) k_s_moments(const Params<real> P, const real* __restrict__ pdf, int lay,
                                                   const int32_t* __restrict__ ipos, int64_t Npad,
                                                   real* __restrict__ rho, real* __restrict__ ux,
                                                   real* __restrict__ uy, real* __restrict__ pdf_eq) {
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= Npad || ipos[c] < 0) return;
-    const real* p = pdf + pdf_index<Q>(c);
     real f[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) f[q] = p[q * kTW];
+    for (int q = 0; q < Q; ++q) f[q] = pdf[pdf_off<Q>(lay, Npad, c, q)];
     real r, x, y;
     moments<real, Q>(f, r, x, y);
     rho[c] = r; ux[c] = x; uy[c] = y;
     const Equilibrium<real, Q> E(r, x, y, P);
-    real* e = pdf_eq + pdf_index<Q>(c);
 #pragma unroll
-    for (int q = 0; q < Q; ++q) e[q * kTW] = E.value(q, P);
+    for (int q = 0; q < Q; ++q) pdf_eq[pdf_off<Q>(lay, Npad, c, q)] = E.value(q, P);
 }
 
 template <typename real>
 struct FaceArgs {
     Params<real> P;
     const real* __restrict__ pdf;
+    int lay; int64_t Npad;
     const int32_t* __restrict__ fcell;     // [F*2] positions, -1 ghost
     const int32_t* __restrict__ fnode;     // [F*2] tracked node ids (ghost faces only)
     const real* __restrict__ fdist;        // [F*2]
@@ -444,11 +566,10 @@ __global__ void __launch_bounds__(256) k_s_faces(const FaceArgs<real> a) {
     const int32_t s0 = a.fcell[2 * j], s1 = a.fcell[2 * j + 1];
     const real d0 = a.fdist[2 * j], d1 = a.fdist[2 * j + 1];
     const real nx = a.fn[2 * j], ny = a.fn[2 * j + 1], L = a.fL[j];
-    const real* p0 = a.pdf + pdf_index<Q>(s0 < 0 ? a.last_pos : (int64_t)s0);
-    const real* p1 = a.pdf + pdf_index<Q>(s1 < 0 ? a.last_pos : (int64_t)s1);
+    const int64_t c0 = s0 < 0 ? a.last_pos : (int64_t)s0, c1 = s1 < 0 ? a.last_pos : (int64_t)s1;
     real f0[Q], f1[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) { f0[q] = p0[q * kTW]; f1[q] = p1[q * kTW]; }
+    for (int q = 0; q < Q; ++q) { f0[q] = a.pdf[pdf_off<Q>(a.lay, a.Npad, c0, q)]; f1[q] = a.pdf[pdf_off<Q>(a.lay, a.Npad, c1, q)]; }
     if (s0 < 0 || s1 < 0) {
         const int32_t na = a.fnode[2 * j], nb = a.fnode[2 * j + 1];
         real g0[Q], g1[Q];
@@ -479,7 +600,7 @@ __global__ void __launch_bounds__(256) k_s_faces(const FaceArgs<real> a) {
 }
 
 template <typename real, int Q, int K>
-__global__ void __launch_bounds__(256) k_s_cells(const Params<real> P, const real* __restrict__ pdf,
+__global__ void __launch_bounds__(256) k_s_cells(const Params<real> P, int lay, const real* __restrict__ pdf,
                                                 const real* __restrict__ pdf_eq, const real* __restrict__ flux,
                                                 const int32_t* __restrict__ cface, const int32_t* __restrict__ csign,
                                                 const int32_t* __restrict__ ipos, int64_t Npad, int64_t No,
@@ -498,12 +619,12 @@ __global__ void __launch_bounds__(256) k_s_cells(const Params<real> P, const rea
 #pragma unroll
         for (int q = 0; q < Q; ++q) fl[q] += flux[j * Q + q] * s;
     }
-    const size_t ix = pdf_index<Q>(c);
     const real ia = inv_area ? inv_area[c] : real(1);        // optional physically consistent mode; NULL = reference
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        const real f = pdf[ix + q * kTW];
-        pdf_out[ix + q * kTW] = f + P.dt * (P.inv_tau * (pdf_eq[ix + q * kTW] - f) - fl[q] * ia);
+        const size_t ix = pdf_off<Q>(lay, Npad, c, q);
+        const real f = pdf[ix];
+        pdf_out[ix] = f + P.dt * (P.inv_tau * (pdf_eq[ix] - f) - fl[q] * ia);
     }
 }
 
@@ -511,35 +632,45 @@ __global__ void __launch_bounds__(256) k_s_cells(const Params<real> P, const rea
 // API-boundary layout conversion
 // ------------------------------------------------------------------------------------------------
 template <typename real, int Q>
-__global__ void k_export_cells(const real* __restrict__ pdf, const int32_t* __restrict__ pos, int64_t N,
+__global__ void k_export_cells(const real* __restrict__ pdf, int lay, int64_t Npad, const int32_t* __restrict__ pos, int64_t N,
                                real* __restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const real* p = pdf + pdf_index<Q>(pos[i]);
+    const int64_t c = pos[i];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) out[i * Q + q] = p[q * kTW];
+    for (int q = 0; q < Q; ++q) out[i * Q + q] = pdf[pdf_off<Q>(lay, Npad, c, q)];
+}
+
+// switch the population layout of a whole buffer (set_option(VARIANT) across layouts)
+template <typename real, int Q>
+__global__ void k_relayout(const real* __restrict__ src, int lay_src, real* __restrict__ dst, int lay_dst, int64_t Npad) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= Npad) return;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) dst[pdf_off<Q>(lay_dst, Npad, c, q)] = src[pdf_off<Q>(lay_src, Npad, c, q)];
 }
 
 template <typename real, int Q>
-__global__ void k_import_cells(real* __restrict__ pdf, const int32_t* __restrict__ pos, int64_t N,
+__global__ void k_import_cells(real* __restrict__ pdf, int lay, int64_t Npad, const int32_t* __restrict__ pos, int64_t N,
                                const real* __restrict__ in) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
-    real* p = pdf + pdf_index<Q>(pos[i]);
+    const int64_t c = pos[i];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) p[q * kTW] = in[i * Q + q];
+    for (int q = 0; q < Q; ++q) pdf[pdf_off<Q>(lay, Npad, c, q)] = in[i * Q + q];
 }
 
 // rho / vel / pdf_eq of the given populations in reference layout (any output may be null)
 template <typename real, int Q>
-__global__ void k_export_moments(const Params<real> P, const real* __restrict__ pdf, const int32_t* __restrict__ pos,
-                                 int64_t N, real* __restrict__ rho, real* __restrict__ vel, real* __restrict__ pdf_eq) {
+__global__ void k_export_moments(const Params<real> P, const real* __restrict__ pdf, int lay, int64_t Npad,
+                                 const int32_t* __restrict__ pos, int64_t N, real* __restrict__ rho, real* __restrict__ vel,
+                                 real* __restrict__ pdf_eq) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const real* p = pdf + pdf_index<Q>(pos[i]);
+    const int64_t c = pos[i];
     real f[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) f[q] = p[q * kTW];
+    for (int q = 0; q < Q; ++q) f[q] = pdf[pdf_off<Q>(lay, Npad, c, q)];
     real r, x, y;
     moments<real, Q>(f, r, x, y);
     if (rho) rho[i] = r;
@@ -553,16 +684,15 @@ __global__ void k_export_moments(const Params<real> P, const real* __restrict__ 
 
 // failure detection: count owned cells with a non-finite population (one atomic per warp)
 template <typename real, int Q>
-__global__ void k_count_nonfinite(const real* __restrict__ pdf, const int32_t* __restrict__ ipos, int64_t Npad, int64_t No,
+__global__ void k_count_nonfinite(const real* __restrict__ pdf, int lay, const int32_t* __restrict__ ipos, int64_t Npad, int64_t No,
                                   unsigned long long* __restrict__ count) {
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool bad = false;
     if (c < Npad) {
         const int32_t o = ipos[c];
         if (o >= 0 && o < No) {
-            const real* p = pdf + pdf_index<Q>(c);
 #pragma unroll
-            for (int q = 0; q < Q; ++q) bad |= !isfinite(p[q * kTW]);
+            for (int q = 0; q < Q; ++q) bad |= !isfinite(pdf[pdf_off<Q>(lay, Npad, c, q)]);
         }
     }
     const unsigned m = __ballot_sync(0xffffffffu, bad);
@@ -571,19 +701,21 @@ __global__ void k_count_nonfinite(const real* __restrict__ pdf, const int32_t* _
 
 // halo exchange helpers: list[i] = position ; buf layout [count][Q]
 template <typename real, int Q>
-__global__ void k_pack(const real* __restrict__ pdf, const int32_t* __restrict__ list, int64_t n, real* __restrict__ buf) {
+__global__ void k_pack(const real* __restrict__ pdf, int lay, int64_t Npad, const int32_t* __restrict__ list, int64_t n,
+                       real* __restrict__ buf) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * Q) return;
     const int64_t i = t / Q; const int q = (int)(t % Q);
-    buf[t] = pdf[pdf_index<Q>(list[i]) + q * kTW];
+    buf[t] = pdf[pdf_off<Q>(lay, Npad, list[i], q)];
 }
 
 template <typename real, int Q>
-__global__ void k_unpack(real* __restrict__ pdf, const int32_t* __restrict__ list, int64_t n, const real* __restrict__ buf) {
+__global__ void k_unpack(real* __restrict__ pdf, int lay, int64_t Npad, const int32_t* __restrict__ list, int64_t n,
+                         const real* __restrict__ buf) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * Q) return;
     const int64_t i = t / Q; const int q = (int)(t % Q);
-    pdf[pdf_index<Q>(list[i]) + q * kTW] = buf[t];
+    pdf[pdf_off<Q>(lay, Npad, list[i], q)] = buf[t];
 }
 
 }  // namespace fvdbm

@@ -81,7 +81,7 @@ def test_config3_square_10M_vs_oracle():
     m, dyn, cells, faces, nodes, _ = bench.build_problem(FULL, FULL, "lax_wendroff")
     assert cells.face_indices.shape[0] == 2 * FULL * FULL
     _run_against_oracle(m, dyn, cells, faces, nodes, "lax_wendroff", (10, 100), f"square nx={FULL}",
-                        variants=(_lib.VARIANT_PAIR, _lib.VARIANT_DIRECT, _lib.VARIANT_TMA))
+                        variants=(_lib.VARIANT_REC, _lib.VARIANT_PAIR, _lib.VARIANT_DIRECT, _lib.VARIANT_TMA))
 
 
 def _cylinder(scale):

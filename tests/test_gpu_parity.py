@@ -20,7 +20,7 @@ from fvdbm_jax_b200 import _lib, meshgen  # noqa: E402
 
 TOL = {np.float32: 1e-5, np.float64: 1e-11}
 MODES = {"tma": ("fused", _lib.VARIANT_TMA), "direct": ("fused", _lib.VARIANT_DIRECT), "pair": ("fused", _lib.VARIANT_PAIR),
-         "staged": ("staged", None)}
+         "rec": ("fused", _lib.VARIANT_REC), "staged": ("staged", None)}
 
 
 def make_env(case, dtype, mode, reorder="none"):
@@ -28,6 +28,8 @@ def make_env(case, dtype, mode, reorder="none"):
     m, variant = MODES[mode]
     if variant == _lib.VARIANT_PAIR and np.dtype(dtype) != np.float32:
         pytest.skip("the packed pair kernel is fp32 only")
+    if variant == _lib.VARIANT_REC and (np.dtype(dtype) != np.float32 or case.Q != 9):
+        pytest.skip("the record-layout kernel is fp32 D2Q9 only")
     env = fb.Environment(cells, faces, nodes, dtype=dtype, mode=m, reorder=reorder)
     env.init()
     if variant is not None:
@@ -46,7 +48,7 @@ def check_state(env, case, step, tol):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("mode", ["pair", "tma", "direct", "staged"])
+@pytest.mark.parametrize("mode", ["rec", "pair", "tma", "direct", "staged"])
 @pytest.mark.parametrize("name", golden.names())
 def test_golden_all_fields(name, mode, dtype):
     case = golden.Case(name)
@@ -59,7 +61,7 @@ def test_golden_all_fields(name, mode, dtype):
     env.close()
 
 
-@pytest.mark.parametrize("mode", ["pair", "direct", "tma", "staged"])
+@pytest.mark.parametrize("mode", ["rec", "pair", "direct", "tma", "staged"])
 @pytest.mark.parametrize("name", golden.names(fp32=True))
 def test_fp32_engine_vs_reference_run_in_fp32(name, mode):
     """*_f32 fixtures = the reference's own code executed with every float in fp32 (what stock JAX
@@ -132,7 +134,10 @@ def test_gpu_bits_equal_the_cpu_walk_of_the_same_operation_sequence(name, dtype)
     case = golden.Case(name)
     s = case.steps[-1]
     cpu = test_hostsim.run(case, dtype, s)
-    for variant in ((_lib.VARIANT_PAIR, _lib.VARIANT_DIRECT, _lib.VARIANT_TMA) if dtype is np.float32 else (_lib.VARIANT_DIRECT,)):
+    variants = (_lib.VARIANT_DIRECT,)
+    if dtype is np.float32:
+        variants = (_lib.VARIANT_PAIR, _lib.VARIANT_DIRECT, _lib.VARIANT_TMA) + ((_lib.VARIANT_REC,) if case.Q == 9 else ())
+    for variant in variants:
         cells, faces, nodes = case.containers()
         env = fb.Environment(cells, faces, nodes, dtype=dtype, mode="fused", reorder="none")
         env.init()
@@ -149,7 +154,8 @@ def test_fused_variants_bitwise_identical():
     renumbering run the same per-cell arithmetic -> bit-identical populations."""
     m, dyn, cells, faces, nodes = _square_problem(64, 48, periodic=True)
     ref = None
-    configs = [dict(variant=_lib.VARIANT_DIRECT), dict(variant=_lib.VARIANT_PAIR), dict(variant=_lib.VARIANT_TMA, tile=128, stages=2),
+    configs = [dict(variant=_lib.VARIANT_DIRECT), dict(variant=_lib.VARIANT_PAIR), dict(variant=_lib.VARIANT_REC),
+               dict(variant=_lib.VARIANT_REC, reverse=1, graph=6, reorder="hilbert", pdl=1), dict(variant=_lib.VARIANT_TMA, tile=128, stages=2),
                dict(variant=_lib.VARIANT_TMA, tile=256, stages=3), dict(variant=_lib.VARIANT_TMA, tile=512, stages=2),
                dict(variant=_lib.VARIANT_TMA, tile=256, stages=4, reverse=1, graph=4),
                dict(variant=_lib.VARIANT_DIRECT, reverse=1, graph=2, reorder="hilbert"),
@@ -298,7 +304,7 @@ def test_full_size_properties():
     prev = np.empty((n, 9), np.float32)
     env.get_into("cells.pdf", prev)                     # current
     assert env.info(_lib.INFO_VARIANT) == (_lib.VARIANT_PAIR if n >= 1 << 22 else _lib.VARIANT_DIRECT)   # default kernel produced `a`
-    for variant, reverse in ((_lib.VARIANT_TMA, 0), (_lib.VARIANT_DIRECT, 1), (_lib.VARIANT_PAIR, 1)):
+    for variant, reverse in ((_lib.VARIANT_TMA, 0), (_lib.VARIANT_DIRECT, 1), (_lib.VARIANT_PAIR, 1), (_lib.VARIANT_REC, 0)):
         env.set_option(_lib.OPT_VARIANT, variant).set_option(_lib.OPT_REVERSE_SWEEP, reverse)
         assert env.info(_lib.INFO_VARIANT) == variant
         env.cells.pdf = f0

@@ -4,7 +4,7 @@ bulk copies (UBLKCP).   python tools/sass_summary.py > profiles/sass_summary.txt
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "fvdbm_jax_b200", "libfvdbm_b200.so")
-KERNELS = ["k_fused_pairILi9ELi3ELi1E", "k_fused_pairILi9ELi3ELi0E", "k_fused_directIfLi9ELi3ELi1E", "k_fused_directIdLi9ELi3ELi1E",
+KERNELS = ["k_fused_recILi3ELi1E", "k_fused_recILi3ELi0E", "k_fused_pairILi9ELi3ELi1E", "k_fused_pairILi9ELi3ELi0E", "k_fused_directIfLi9ELi3ELi1E", "k_fused_directIdLi9ELi3ELi1E",
            "k_fused_tmaIfLi9ELi3ELi1E", "k_nodesIfLi9E"]
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 blocks = re.split(r"\n\s*Function : ", out)
