@@ -319,7 +319,6 @@ struct EngineT final : Engine {
 
     int sanitize_options() {
         if (variant != FVDBM_VARIANT_DIRECT && variant != FVDBM_VARIANT_TMA && variant != FVDBM_VARIANT_PAIR && variant != FVDBM_VARIANT_REC) { err = "unknown variant"; return FVDBM_ERR_ARG; }
-        if (variant == FVDBM_VARIANT_REC && !rec_available()) { err = "the record-layout kernel exists for fp32 D2Q9 only"; return FVDBM_ERR_ARG; }
         if (variant == FVDBM_VARIANT_REC && mode != FVDBM_MODE_FUSED) { err = "the record-layout kernel needs the fused mode"; return FVDBM_ERR_ARG; }
         if (variant == FVDBM_VARIANT_PAIR && sizeof(real) != 4) { err = "the packed two-cells-per-thread kernel exists for fp32 only"; return FVDBM_ERR_ARG; }
         if (tile_cells != 128 && tile_cells != 256 && tile_cells != 512) { err = "tile_cells must be 128, 256 or 512"; return FVDBM_ERR_ARG; }
@@ -341,6 +340,7 @@ struct EngineT final : Engine {
         a.G.npdf = npdf.p; a.G.NTpad = plan.NTpad;
         a.cell_begin = begin; a.cell_end = end;
         a.reverse = (reverse_sweep && cur == 1) ? 1 : 0;
+        a.Npad = plan.Npad;
         a.prefetch_dist = prefetch_dist;
         return a;
     }
@@ -370,7 +370,7 @@ struct EngineT final : Engine {
         } else if (variant == FVDBM_VARIANT_PAIR) {
             launch_pair(a, end - begin, st);
         } else if (variant == FVDBM_VARIANT_DIRECT) {
-            CU_TRY(launch_k(k_fused_direct<real, Q, K, SCHEME>, blocks_for(end - begin, 256), 256, 0, st, pdl_chain(), a));
+            CU_TRY(launch_k(k_fused_direct<real, Q, K, SCHEME, 0>, blocks_for(end - begin, 256), 256, 0, st, pdl_chain(), a));
         } else {
             const size_t smem = kTmaHeader + (size_t)stages * stage_bytes(tile_cells);
             int per_sm = ctas_per_sm;
@@ -396,12 +396,15 @@ struct EngineT final : Engine {
         launch_k(k_fused_pair<Q, K, SCHEME>, blocks_for(cells / 2, FVDBM_PAIR_THREADS), FVDBM_PAIR_THREADS, 0, st, pdl_chain(), a);
     }
     void launch_pair(const FusedArgs<double>&, int64_t, cudaStream_t) {}
-    // fp32 D2Q9 only: thread per cell over the record layout
+    // record layout: packed k_fused_rec for fp32 D2Q9, the thread-per-cell kernel over records otherwise
     void launch_rec(const FusedArgs<float>& a, int64_t cells, cudaStream_t st) {
-        if constexpr (Q == 9) launch_k(k_fused_rec<K, SCHEME>, blocks_for(cells, 256), 256, 0, st, pdl_chain(), a, plan.Npad);
+        if constexpr (Q == 9) launch_k(k_fused_rec<K, SCHEME>, blocks_for(cells, FVDBM_REC_THREADS), FVDBM_REC_THREADS, 0, st, pdl_chain(), a);
+        else launch_k(k_fused_direct<float, Q, K, SCHEME, 1>, blocks_for(cells, 256), 256, 0, st, pdl_chain(), a);
     }
-    void launch_rec(const FusedArgs<double>&, int64_t, cudaStream_t) {}
-    static constexpr bool rec_available() { return sizeof(real) == 4 && Q == 9; }
+    void launch_rec(const FusedArgs<double>& a, int64_t cells, cudaStream_t st) {
+        launch_k(k_fused_direct<double, Q, K, SCHEME, 1>, blocks_for(cells, 256), 256, 0, st, pdl_chain(), a);
+    }
+    static constexpr bool rec_available() { return true; }
 
     // the population buffers follow the variant's layout; switching re-lays both out (rare: set_option only)
     int set_layout(int want) {

@@ -24,6 +24,7 @@ struct FusedArgs {
     GhostTables<real> G;               // boundary sides + tracked node populations
     int64_t cell_begin, cell_end;      // position range, multiples of PAD_TO (512)
     int reverse;                       // 1: sweep tiles from the top (L2 reuse of last step's writes)
+    int64_t Npad;                      // padded position count (record layout: offset of the rest populations)
     int prefetch_dist;                 // >0: every CTA asks L2 to prefetch the streaming operands of the CTA
                                        // `prefetch_dist` blocks ahead (cp.async.bulk.prefetch.L2)
 };
@@ -57,23 +58,69 @@ __device__ __forceinline__ void prefetch_cells_l2(const FusedArgs<real>& a, int6
     prefetch_l2_bulk(a.ccoef + mt * (K * NC * kTW), (uint32_t)(cells * K * NC * sizeof(real)));
     prefetch_l2_bulk(a.ccode + mt * (K * kTW), (uint32_t)(cells * K * sizeof(int32_t)));
 }
+// same for the record layout: records and rest populations of the run are two contiguous blocks
+template <typename real, int Q, int K, int NC>
+__device__ __forceinline__ void prefetch_cells_rec_l2(const FusedArgs<real>& a, int64_t first_cell, int cells) {
+    if (first_cell < a.cell_begin || first_cell + cells > a.cell_end) return;
+    const size_t mt = (size_t)(first_cell >> 5);
+    prefetch_l2_bulk(a.pdf_in + (size_t)first_cell * (Q - 1), (uint32_t)(cells * (Q - 1) * sizeof(real)));
+    prefetch_l2_bulk(a.pdf_in + (size_t)a.Npad * (Q - 1) + first_cell, (uint32_t)(cells * sizeof(real)));
+    prefetch_l2_bulk(a.ccoef + mt * (K * NC * kTW), (uint32_t)(cells * K * NC * sizeof(real)));
+    prefetch_l2_bulk(a.ccode + mt * (K * kTW), (uint32_t)(cells * K * sizeof(int32_t)));
+}
 
 // measured on B200 (profiles/r1_experiment_occupancy_cachehints.txt): fp32 is best left to ptxas
 // (5 CTAs/SM; forcing 6 or 8 CTAs spills and loses 2-18 %), fp64 gains 15 % from 3 CTAs/SM.
 #define FVDBM_DIRECT_BOUNDS __launch_bounds__(256, (sizeof(real) == 8 ? 3 : (Q == 9 ? 5 : 4)))
 
+// record layout (core.cuh: lay 1): the Q-1 moving populations of `cell` with 128-bit accesses
+template <int Q>
+__device__ __forceinline__ void load_record(const float* __restrict__ base, int64_t cell, float* out) {      // out[1..Q-1]
+    const float4* p = reinterpret_cast<const float4*>(base) + cell * ((Q - 1) / 4);
+#pragma unroll
+    for (int i = 0; i < (Q - 1) / 4; ++i) {
+        const float4 v = __ldg(p + i);
+        out[1 + 4 * i] = v.x; out[2 + 4 * i] = v.y; out[3 + 4 * i] = v.z; out[4 + 4 * i] = v.w;
+    }
+}
+template <int Q>
+__device__ __forceinline__ void load_record(const double* __restrict__ base, int64_t cell, double* out) {
+    const double2* p = reinterpret_cast<const double2*>(base) + cell * ((Q - 1) / 2);
+#pragma unroll
+    for (int i = 0; i < (Q - 1) / 2; ++i) {
+        const double2 v = __ldg(p + i);
+        out[1 + 2 * i] = v.x; out[2 + 2 * i] = v.y;
+    }
+}
+template <int Q>
+__device__ __forceinline__ void store_record(float* __restrict__ base, int64_t cell, const float* in) {
+    float4* p = reinterpret_cast<float4*>(base) + cell * ((Q - 1) / 4);
+#pragma unroll
+    for (int i = 0; i < (Q - 1) / 4; ++i) p[i] = make_float4(in[1 + 4 * i], in[2 + 4 * i], in[3 + 4 * i], in[4 + 4 * i]);
+}
+template <int Q>
+__device__ __forceinline__ void store_record(double* __restrict__ base, int64_t cell, const double* in) {
+    double2* p = reinterpret_cast<double2*>(base) + cell * ((Q - 1) / 2);
+#pragma unroll
+    for (int i = 0; i < (Q - 1) / 2; ++i) p[i] = make_double2(in[1 + 2 * i], in[2 + 2 * i]);
+}
+
 // ------------------------------------------------------------------------------------------------
-// V1: thread per cell, everything through L1/L2.
+// V1: thread per cell, everything through L1/L2.  LAY = 0: tiled AoSoA populations; LAY = 1: record layout
+// (neighbour gathers are (Q-1)*sizeof(real)/16 128-bit loads from one or two sectors; fp64 and D2Q13 use this
+// kernel for FVDBM_VARIANT_REC, fp32 D2Q9 has the packed k_fused_rec below).
 // ------------------------------------------------------------------------------------------------
-template <typename real, int Q, int K, int SCHEME>
+template <typename real, int Q, int K, int SCHEME, int LAY>
 __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     constexpr int NC = SCHEME == 0 ? 2 : 4;
     const int64_t nblk = gridDim.x;
     const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
     const int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
-    if (a.prefetch_dist > 0 && threadIdx.x == 0)
-        prefetch_cells_l2<real, Q, K, NC>(a, a.cell_begin + (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x,
-                                          (int)blockDim.x);
+    if (a.prefetch_dist > 0 && threadIdx.x == 0) {
+        const int64_t first = a.cell_begin + (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x;
+        if (LAY == 0) prefetch_cells_l2<real, Q, K, NC>(a, first, (int)blockDim.x);
+        else prefetch_cells_rec_l2<real, Q, K, NC>(a, first, (int)blockDim.x);
+    }
     if (c >= a.cell_end) return;
     const size_t tile = (size_t)(c >> 5);
     const int lane = (int)(c & 31);
@@ -90,10 +137,15 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     const real* gco = a.ccoef + tile * (K * NC * kTW) + lane;
 #pragma unroll
     for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
-    const real* gp = a.pdf_in + tile * (Q * kTW) + lane;
     real f[Q], out[Q];
+    if (LAY == 0) {
+        const real* gp = a.pdf_in + tile * (Q * kTW) + lane;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) f[q] = __ldg(gp + q * kTW);
+        for (int q = 0; q < Q; ++q) f[q] = __ldg(gp + q * kTW);
+    } else {
+        load_record<Q>(a.pdf_in, c, f);
+        f[0] = __ldg(a.pdf_in + (size_t)a.Npad * (Q - 1) + c);
+    }
     const bool live = code[0] != kHole;
     if (!live) code[0] = 0;                        // neutral: interior side towards position 0
     // PDL: everything above reads data older than the predecessor (the node kernel); only the ghost sides below read
@@ -102,15 +154,22 @@ __global__ void FVDBM_DIRECT_BOUNDS k_fused_direct(const FusedArgs<real> a) {
     pdl_trigger();
     const real* pin = a.pdf_in;
     auto gather = [pin](int64_t nb, real* fn) {
-        const real* pn = pin + pdf_index<Q>(nb);
+        if (LAY == 0) {
+            const real* pn = pin + pdf_index<Q>(nb);
 #pragma unroll
-        for (int q = 1; q < Q; ++q) fn[q] = __ldg(pn + q * kTW);
+            for (int q = 1; q < Q; ++q) fn[q] = __ldg(pn + q * kTW);
+        } else load_record<Q>(pin, nb, fn);
     };
     advance_cell<real, Q, K, SCHEME>(a.P, a.G, f, code, coef, gather, out);
-    real* go = a.pdf_out + tile * (Q * kTW) + lane;
     if (live) {
+        if (LAY == 0) {
+            real* go = a.pdf_out + tile * (Q * kTW) + lane;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) go[q * kTW] = out[q];
+            for (int q = 0; q < Q; ++q) go[q * kTW] = out[q];
+        } else {
+            store_record<Q>(a.pdf_out, c, out);
+            a.pdf_out[(size_t)a.Npad * (Q - 1) + c] = out[0];
+        }
     }
 }
 
@@ -211,23 +270,23 @@ __global__ void __launch_bounds__(FVDBM_PAIR_THREADS, FVDBM_PAIR_MINCTAS) k_fuse
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
 
+#ifndef FVDBM_REC_THREADS
+#define FVDBM_REC_THREADS 256
+#endif
+#ifndef FVDBM_REC_MINCTAS
+#define FVDBM_REC_MINCTAS 3
+#endif
 template <int K, int SCHEME>
-__global__ void __launch_bounds__(256, 3) k_fused_rec(const FusedArgs<float> a, const int64_t Npad) {
+__global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_REC_MINCTAS) k_fused_rec(const FusedArgs<float> a) {
     constexpr int Q = 9, NC = SCHEME == 0 ? 2 : 4;
+    const int64_t Npad = a.Npad;
     const int64_t nblk = gridDim.x;
     const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
     const int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
     const float* rest_in = a.pdf_in + (size_t)Npad * (Q - 1);
-    if (a.prefetch_dist > 0 && threadIdx.x == 0) {
-        const int64_t first = a.cell_begin + (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x;
-        if (first >= a.cell_begin && first + blockDim.x <= a.cell_end) {
-            const size_t mt = (size_t)(first >> 5);
-            prefetch_l2_bulk(a.pdf_in + (size_t)first * (Q - 1), (uint32_t)(blockDim.x * (Q - 1) * sizeof(float)));
-            prefetch_l2_bulk(rest_in + first, (uint32_t)(blockDim.x * sizeof(float)));
-            prefetch_l2_bulk(a.ccoef + mt * (K * NC * kTW), (uint32_t)(blockDim.x * K * NC * sizeof(float)));
-            prefetch_l2_bulk(a.ccode + mt * (K * kTW), (uint32_t)(blockDim.x * K * sizeof(int32_t)));
-        }
-    }
+    if (a.prefetch_dist > 0 && threadIdx.x == 0)
+        prefetch_cells_rec_l2<float, Q, K, NC>(a, a.cell_begin + (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x,
+                                               (int)blockDim.x);
     if (c >= a.cell_end) return;
     const size_t tile = (size_t)(c >> 5);
     const int lane = (int)(c & 31);

@@ -61,9 +61,10 @@ extern "C" {
 #define FVDBM_VARIANT_TMA    2   /* persistent CTAs, cp.async.bulk + mbarrier tile pipeline   */
 #define FVDBM_VARIANT_PAIR   3   /* fp32 only: two cells per thread, packed FFMA2 math, 64-bit
                                     coalesced streaming accesses                              */
-#define FVDBM_VARIANT_REC    4   /* fp32 D2Q9 only: thread per cell over the RECORD layout (a cell's 8 moving
-                                    populations = one 32-byte sector: neighbour gathers are 2 x 128-bit loads
-                                    from one sector), arithmetic packed over population pairs (FFMA2)          */
+#define FVDBM_VARIANT_REC    4   /* thread per cell over the RECORD layout (a cell's Q-1 moving populations are
+                                    contiguous -- one 32-byte sector for fp32 D2Q9 -- so a neighbour gather is
+                                    a few 128-bit loads from one or two sectors); fp32 D2Q9 additionally packs
+                                    the arithmetic over population pairs (FFMA2)                              */
 /* All variants execute the same canonical operation sequence: results are bit-identical.
  * Debug / A-B environment overrides read once at fvdbm_create (each mirrors an fvdbm_option):
  *   FVDBM_VARIANT, FVDBM_TILE_CELLS, FVDBM_STAGES, FVDBM_GRAPH_STEPS, FVDBM_CTAS_PER_SM,

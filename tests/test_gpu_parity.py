@@ -28,8 +28,6 @@ def make_env(case, dtype, mode, reorder="none"):
     m, variant = MODES[mode]
     if variant == _lib.VARIANT_PAIR and np.dtype(dtype) != np.float32:
         pytest.skip("the packed pair kernel is fp32 only")
-    if variant == _lib.VARIANT_REC and (np.dtype(dtype) != np.float32 or case.Q != 9):
-        pytest.skip("the record-layout kernel is fp32 D2Q9 only")
     env = fb.Environment(cells, faces, nodes, dtype=dtype, mode=m, reorder=reorder)
     env.init()
     if variant is not None:
@@ -134,9 +132,9 @@ def test_gpu_bits_equal_the_cpu_walk_of_the_same_operation_sequence(name, dtype)
     case = golden.Case(name)
     s = case.steps[-1]
     cpu = test_hostsim.run(case, dtype, s)
-    variants = (_lib.VARIANT_DIRECT,)
+    variants = (_lib.VARIANT_DIRECT, _lib.VARIANT_REC)
     if dtype is np.float32:
-        variants = (_lib.VARIANT_PAIR, _lib.VARIANT_DIRECT, _lib.VARIANT_TMA) + ((_lib.VARIANT_REC,) if case.Q == 9 else ())
+        variants = (_lib.VARIANT_PAIR, _lib.VARIANT_DIRECT, _lib.VARIANT_TMA, _lib.VARIANT_REC)
     for variant in variants:
         cells, faces, nodes = case.containers()
         env = fb.Environment(cells, faces, nodes, dtype=dtype, mode="fused", reorder="none")

@@ -37,6 +37,8 @@ def main():
     env.init(); env.build()
     for variant in [int(v) for v in args.variants.split(",")]:
         for dist in [int(d) for d in args.dists.split(",")]:
+            if variant == 3 and args.dtype == "f64":
+                continue
             env.set_option(_lib.OPT_VARIANT, variant).set_option(_lib.OPT_PREFETCH_DIST, dist)
             env.step(20); env.sync()
             burst = min(env.step_timed(50) for _ in range(3)) / 50
