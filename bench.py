@@ -537,7 +537,7 @@ def main():
     iter_ms = ms / (inner * args.steps)
     achieved = n_local * b_alg / (iter_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": {1: "k_fused_direct", 2: "k_fused_tma", 3: "k_fused_pair"}.get(n_launch_info, "?"),
+                "traffic": None, "kernel": {1: "k_fused_direct", 2: "k_fused_tma", 3: "k_fused_pair", 4: "k_fused_rec"}.get(n_launch_info, "?"),
                 "algorithmic_bytes_per_cell_update": b_alg, "cells_per_launch": n_local, "avg_launch_ms": iter_ms,
                 "peak_source": peak_src,
                 "note": "avg_launch_ms = event time / iterations (includes the O(sqrt N) node + border launches that run "

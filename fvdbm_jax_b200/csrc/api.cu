@@ -307,12 +307,19 @@ struct EngineT final : Engine {
     }
     size_t max_smem = 0;
     int occ_cache = 0;
-    // fp32, >= 4M owned cells (bandwidth-bound regime): the packed two-cells-per-thread kernel -- same speed as the
-    // thread-per-cell kernel at the DRAM limit with half the instructions issued.  Smaller meshes are latency-bound
-    // (node kernel -> border cells chain); there the shorter per-thread critical path of the thread-per-cell kernel
-    // wins by 3-25 % (profiles/r2_small_configs_by_variant.jsonl).  fp64: thread-per-cell.
+    // fp32 D2Q9: the record-layout kernel (single-sector 128-bit gathers, FFMA2 over population pairs) where it
+    // measured fastest -- the bandwidth-bound regime (>= 4M owned cells: 0.2257 vs 0.2309 (direct) / 0.2362 (pair) ms
+    // sustained per 10M-cell iteration on one box) and very small meshes (<= 64k cells: 5.3-5.6 vs 5.7-6.0 us/step);
+    // in between the thread-per-cell AoSoA kernel is as fast or faster (2M-cell porous: 51.0 vs 52.5 us).
+    // fp32 D2Q13 >= 4M cells: the packed two-cells-per-thread kernel.  fp64: thread-per-cell AoSoA (the fp64 record
+    // is 64 B and its strided 128-bit accesses lose: 0.518 vs 0.359 ms).   profiles/r2_ab_record_kernel.jsonl
     int default_variant() const {
-        return (sizeof(real) == 4 && plan.No >= (int64_t(1) << 22)) ? FVDBM_VARIANT_PAIR : FVDBM_VARIANT_DIRECT;
+        if (sizeof(real) == 4 && mode == FVDBM_MODE_FUSED) {
+            const bool big = plan.No >= (int64_t(1) << 22);
+            if (Q == 9 && (big || plan.No <= (int64_t(1) << 16))) return FVDBM_VARIANT_REC;
+            if (big) return FVDBM_VARIANT_PAIR;
+        }
+        return FVDBM_VARIANT_DIRECT;
     }
 
     size_t stage_bytes(int tc) const { return tma_stage_bytes<real, Q, K, SCHEME>(tc); }

@@ -274,7 +274,7 @@ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y
 #define FVDBM_REC_THREADS 256
 #endif
 #ifndef FVDBM_REC_MINCTAS
-#define FVDBM_REC_MINCTAS 3
+#define FVDBM_REC_MINCTAS 5           // A/B on B200: 256x5 (48 regs, no spills) 0.2058 ms sustained vs 256x3/4 (56 regs) 0.2093, 128x8 0.2072
 #endif
 template <int K, int SCHEME>
 __global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_REC_MINCTAS) k_fused_rec(const FusedArgs<float> a) {
