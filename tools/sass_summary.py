@@ -26,6 +26,6 @@ for k in KERNELS:
             tot = sum(ops.values())
             print(f"{name}\n  total {tot}: " + ", ".join(f"{o} {c}" for o, c in ops.most_common(28)))
             keys = ["FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "FSEL", "DFMA", "DADD", "DMUL", "LDG.32", "LDG.64", "LDG.128", "STG.32",
-                    "STG.64", "UBLKPF", "UBLKCP", "SYNCS", "SHFL"]
+                    "STG.64", "STG.128", "UBLKPF", "UBLKCP", "SYNCS", "SHFL"]
             print("  key: " + ", ".join(f"{x}={ops.get(x, 0)}" for x in keys) + "\n")
             break
