@@ -315,8 +315,8 @@ struct EngineT final : Engine {
     // is 64 B and its strided 128-bit accesses lose: 0.518 vs 0.359 ms).   profiles/r2_ab_record_kernel.jsonl
     int default_variant() const {
         if (sizeof(real) == 4 && mode == FVDBM_MODE_FUSED) {
-            const bool big = plan.No >= (int64_t(1) << 22);
-            if (Q == 9 && (big || plan.No <= (int64_t(1) << 16))) return FVDBM_VARIANT_REC;
+            const bool big = plan.No >= (int64_t(1) << 22), small = plan.No <= (int64_t(1) << 16);
+            if ((Q == 9 && big) || small) return FVDBM_VARIANT_REC;      // (D2Q13 <= 64k: thread-per-cell over records, 5.63 vs 6.01 us)
             if (big) return FVDBM_VARIANT_PAIR;
         }
         return FVDBM_VARIANT_DIRECT;

@@ -56,8 +56,9 @@ extern "C" {
 #define FVDBM_MODE_FUSED  2   /* node kernel + one cell-centric kernel per step                   */
 
 /* fused-kernel variants (fvdbm_set_option(h, FVDBM_OPT_VARIANT, v)) */
-#define FVDBM_VARIANT_AUTO   0   /* fp32 D2Q9 with >= 4M or <= 64k owned cells: REC; fp32 D2Q13 >= 4M: PAIR;
-                                    otherwise DIRECT (measured choices, api.cu: default_variant)              */
+#define FVDBM_VARIANT_AUTO   0   /* fp32: REC for D2Q9 with >= 4M owned cells and for any lattice with <= 64k;
+                                    PAIR for D2Q13 >= 4M; otherwise (and fp64) DIRECT -- measured choices,
+                                    api.cu: default_variant                                                   */
 #define FVDBM_VARIANT_DIRECT 1   /* thread per cell, all operands through L1/L2               */
 #define FVDBM_VARIANT_TMA    2   /* persistent CTAs, cp.async.bulk + mbarrier tile pipeline   */
 #define FVDBM_VARIANT_PAIR   3   /* fp32 only: two cells per thread, packed FFMA2 math, 64-bit
