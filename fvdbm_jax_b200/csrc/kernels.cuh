@@ -261,14 +261,25 @@ __global__ void __launch_bounds__(FVDBM_PAIR_THREADS, FVDBM_PAIR_MINCTAS) k_fuse
 
 // ------------------------------------------------------------------------------------------------
 // V4 (fp32, D2Q9): thread per cell over the RECORD layout (core.cuh: lay 1).  The eight moving populations of a
-// cell are one 32-byte sector, so a neighbour gather is two LDG.E.128 from ONE sector (the AoSoA kernels touch
-// eight sectors with eight LDG.E.32), the own populations are two LDG.E.128 + one LDG.E.32, the result two
-// STG.E.128 + one STG.E.32; and the arithmetic is packed over POPULATION pairs (q1,q2) (q3,q4) (q5,q6) (q7,q8):
+// cell are one 32-byte sector, so a neighbour gather is ONE 256-bit load (LDG.E.ENL2.256) of ONE sector (the
+// AoSoA kernels touch eight sectors with eight LDG.E.32), the own populations are one 256-bit + one 32-bit load,
+// the result one 256-bit + one 32-bit store; and the arithmetic is packed over POPULATION pairs (q1,q2) (q3,q4) (q5,q6) (q7,q8):
 // per side the four distinct KSI.M values form two pairs W0 = (Mx, My), W2 = (Mx+My, My-Mx) and their negations,
 // so c = A - W Gd, f* = f_slot0 + (fn - f) c and fl += f* W are four FFMA2 each, with scalar side coefficients as
 // broadcast operands.  Same canonical operation sequence per (cell, population) as every other kernel -> same bits.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
+// one D2Q9 fp32 record (8 moving populations, 32 bytes, 32-byte aligned) = ONE 256-bit access (sm_100: LDG.E.ENL2.256)
+__device__ __forceinline__ void ld_record256(const float* p, float2* o) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(o[0].x), "=f"(o[0].y), "=f"(o[1].x), "=f"(o[1].y), "=f"(o[2].x), "=f"(o[2].y), "=f"(o[3].x), "=f"(o[3].y)
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_record256(float* p, const float2* o) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(o[0].x), "f"(o[0].y), "f"(o[1].x), "f"(o[1].y), "f"(o[2].x), "f"(o[2].y), "f"(o[3].x), "f"(o[3].y)
+                 : "memory");
+}
 
 #ifndef FVDBM_REC_THREADS
 #define FVDBM_REC_THREADS 256
@@ -298,10 +309,9 @@ __global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_REC_MINCTAS) k_fused_
     const float* gco = a.ccoef + tile * (K * NC * kTW) + lane;
 #pragma unroll
     for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
-    const float4* rec = reinterpret_cast<const float4*>(a.pdf_in) + 2 * c;
-    const float4 ra = __ldg(rec), rb = __ldg(rec + 1);
+    float2 f[4];                                                                          // (q1,q2) (q3,q4) (q5,q6) (q7,q8)
+    ld_record256(a.pdf_in + (size_t)c * (Q - 1), f);
     const float f0 = __ldg(rest_in + c);
-    const float2 f[4] = {f2(ra.x, ra.y), f2(ra.z, ra.w), f2(rb.x, rb.y), f2(rb.z, rb.w)};     // (q1,q2) (q3,q4) (q5,q6) (q7,q8)
     const bool live = code[0] != kHole;
     if (!live) code[0] = 0;                        // neutral: interior side towards position 0
     pdl_wait();
@@ -312,9 +322,7 @@ __global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_REC_MINCTAS) k_fused_
         const int32_t cd = code[k];
         float2 fn[4];
         if (cd >= 0) {
-            const float4* rn = reinterpret_cast<const float4*>(a.pdf_in) + 2 * (int64_t)(cd >> 2);
-            const float4 na = __ldg(rn), nb = __ldg(rn + 1);
-            fn[0] = f2(na.x, na.y); fn[1] = f2(na.z, na.w); fn[2] = f2(nb.x, nb.y); fn[3] = f2(nb.z, nb.w);
+            ld_record256(a.pdf_in + (size_t)(cd >> 2) * (Q - 1), fn);
         } else {                                    // ghost side (border cells only): scalar path of core.cuh
             const float fo[Q] = {f0, f[0].x, f[0].y, f[1].x, f[1].y, f[2].x, f[2].y, f[3].x, f[3].y};
             float g[Q];
@@ -375,9 +383,7 @@ __global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_REC_MINCTAS) k_fused_
     const float g0 = v_fma(wr0, base, -f0);                            // poly_0 == base exactly (KSI_0 = 0)
     const float out0 = v_fma(a.P.dt, v_fma(a.P.inv_tau, g0, -0.0f), f0);
     if (live) {
-        float4* ro = reinterpret_cast<float4*>(a.pdf_out) + 2 * c;
-        ro[0] = make_float4(out[0].x, out[0].y, out[1].x, out[1].y);
-        ro[1] = make_float4(out[2].x, out[2].y, out[3].x, out[3].y);
+        st_record256(a.pdf_out + (size_t)c * (Q - 1), out);
         a.pdf_out[(size_t)Npad * (Q - 1) + c] = out0;
     }
 }
