@@ -1,5 +1,5 @@
 """Opcode histogram of the hot kernels in the shipped library (cuobjdump -sass), the evidence for
-packed math (FFMA2/FADD2/FMUL2), wide accesses (LDG.E.64 / STG.E.64), L2 bulk prefetch (UBLKPF) and TMA
+packed math (FFMA2/FADD2/FMUL2), wide accesses (LDG.E.64 / STG.E.64, LDG.E.ENL2.256 / STG.E.ENL2.256), L2 bulk prefetch (UBLKPF) and TMA
 bulk copies (UBLKCP).   python tools/sass_summary.py > profiles/sass_summary.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,12 +20,12 @@ for k in KERNELS:
                 op = m.group(1)
                 base = op.split(".")[0]
                 if base in ("LDG", "STG", "LDS", "STS"):
-                    w = re.search(r"\.(64|128)", op)
+                    w = re.search(r"\.(64|128|256)", op)
                     base += "." + (w.group(1) if w else "32")
                 ops[base] += 1
             tot = sum(ops.values())
             print(f"{name}\n  total {tot}: " + ", ".join(f"{o} {c}" for o, c in ops.most_common(28)))
-            keys = ["FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "FSEL", "DFMA", "DADD", "DMUL", "LDG.32", "LDG.64", "LDG.128", "STG.32",
-                    "STG.64", "STG.128", "UBLKPF", "UBLKCP", "SYNCS", "SHFL"]
+            keys = ["FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "FSEL", "DFMA", "DADD", "DMUL", "LDG.32", "LDG.64", "LDG.128", "LDG.256", "STG.32",
+                    "STG.64", "STG.128", "STG.256", "UBLKPF", "UBLKCP", "SYNCS", "SHFL"]
             print("  key: " + ", ".join(f"{x}={ops.get(x, 0)}" for x in keys) + "\n")
             break
