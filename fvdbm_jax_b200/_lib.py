@@ -32,8 +32,18 @@ EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_err
            "fvdbm_set_params",
            "fvdbm_set_option", "fvdbm_info", "fvdbm_check_finite", "fvdbm_halo_set_lists", "fvdbm_halo_pack",
            "fvdbm_halo_unpack", "fvdbm_step_phase", "fvdbm_stream", "fvdbm_comm_unique_id", "fvdbm_comm_init",
-           "fvdbm_halo_set_peers", "fvdbm_sfc_keys", "fvdbm_plan_create",
+           "fvdbm_halo_set_peers", "fvdbm_sfc_keys", "fvdbm_mesh_ring_width", "fvdbm_mesh_properties", "fvdbm_plan_create",
            "fvdbm_plan_destroy", "fvdbm_plan_array", "fvdbm_plan_scalar")
+
+
+class MeshDesc(C.Structure):
+    """fvdbm_mesh_desc (include/fvdbm_b200.h): raw triangle mesh in, Mesher attributes out."""
+    _fields_ = [("N", C.c_int64), ("F", C.c_int64), ("P", C.c_int64), ("M", C.c_int32), ("reserved", C.c_int32)] + [
+        (name, C.c_void_p) for name in (
+            "points", "cells", "faces", "point_alias", "cell_centers", "cell_face_indices", "cell_face_normals",
+            "cell_face_normal_signs", "faces_out", "face_centers", "face_normals", "face_lengths", "face_cell_indices",
+            "face_cell_center_distances", "stencil_norms", "cc_stencil_dist", "face_stencil_angles",
+            "point_cell_indices", "point_cell_center_distances")]
 
 
 class Desc(C.Structure):
@@ -101,6 +111,10 @@ def load():
     lib.fvdbm_stream.restype = C.c_void_p
     lib.fvdbm_sfc_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.fvdbm_sfc_keys.restype = C.c_int
+    lib.fvdbm_mesh_ring_width.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    lib.fvdbm_mesh_ring_width.restype = C.c_int64
+    lib.fvdbm_mesh_properties.argtypes = [C.POINTER(MeshDesc)]
+    lib.fvdbm_mesh_properties.restype = C.c_int
     lib.fvdbm_plan_create.argtypes = [C.POINTER(Desc), C.POINTER(P)]
     lib.fvdbm_plan_destroy.argtypes = [P]
     lib.fvdbm_plan_destroy.restype = None

@@ -57,7 +57,10 @@ class Container:
 
     def __init__(self, size, dynamics: Dynamics):
         eq = dynamics.calc_eq(np.float64(1), np.zeros(dynamics.DIM))
-        self.pdf = np.repeat(np.asarray(eq)[np.newaxis], size, axis=0)
+        # every row = W: a read-only broadcast view (the reference's jnp arrays are immutable too; assign a new array to
+        # change it) instead of 2 GB of identical rows at 10^7 cells; consumers copy on conversion
+        eq = np.asarray(eq)
+        self.pdf = np.broadcast_to(eq, (size,) + eq.shape)
         self.dynamics = dynamics
 
     def __repr__(self):

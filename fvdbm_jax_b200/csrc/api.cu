@@ -21,6 +21,7 @@ typedef enum { ncclFloat32 = 7, ncclFloat64 = 8 } ncclDataType_t;
 
 #include "../../include/fvdbm_b200.h"
 #include "plan.hpp"
+#include "mesh.hpp"
 #include "kernels.cuh"
 
 using namespace fvdbm;
@@ -1069,6 +1070,43 @@ int fvdbm_sfc_keys(const double* points, const int32_t* elements, int64_t ncells
         keys[c] = d;
     }
     return FVDBM_OK;
+}
+
+// ---- host-only Mesher-equivalent (csrc/mesh.hpp) ---------------------------------------------------
+int64_t fvdbm_mesh_ring_width(const int32_t* cells, const int32_t* point_alias, int64_t N, int64_t P) {
+    if ((!cells && N > 0) || N < 0 || P < 0) { g_create_error = "bad argument"; return FVDBM_ERR_ARG; }
+    const int64_t m = fvdbm::mesh_ring_width(cells, point_alias, N, P);
+    if (m < 0) g_create_error = "point id out of range";
+    return m;
+}
+
+int fvdbm_mesh_properties(const fvdbm_mesh_desc* d) {
+    if (!d) { g_create_error = "null argument"; return FVDBM_ERR_ARG; }
+    const bool has_c = d->N > 0, has_f = d->F > 0, has_r = d->P > 0 && d->M > 0;
+    if (d->N < 0 || d->F < 0 || d->P < 0 || d->M < 0 || (d->P > 0 && !d->points) || (has_c && !d->cells) || (has_f && !d->faces) ||
+        (has_c && (!d->cell_centers || !d->cell_face_indices || !d->cell_face_normals || !d->cell_face_normal_signs)) ||
+        (has_f && (!d->faces_out || !d->face_centers || !d->face_normals || !d->face_lengths || !d->face_cell_indices ||
+                   !d->face_cell_center_distances || !d->stencil_norms || !d->cc_stencil_dist || !d->face_stencil_angles)) ||
+        (has_r && (!d->point_cell_indices || !d->point_cell_center_distances))) {
+        g_create_error = "fvdbm_mesh_properties: null array";
+        return FVDBM_ERR_ARG;
+    }
+    fvdbm::MeshIn in;
+    in.N = d->N; in.F = d->F; in.P = d->P;
+    in.points = d->points; in.cells = d->cells; in.faces = d->faces; in.alias = d->point_alias;
+    fvdbm::MeshOut o;
+    o.M = d->M;
+    o.cell_centers = d->cell_centers; o.cell_face_indices = d->cell_face_indices; o.cell_face_normals = d->cell_face_normals;
+    o.cell_face_normal_signs = d->cell_face_normal_signs; o.faces = d->faces_out; o.face_centers = d->face_centers;
+    o.face_normals = d->face_normals; o.face_lengths = d->face_lengths; o.face_cell_indices = d->face_cell_indices;
+    o.face_cell_center_distances = d->face_cell_center_distances; o.stencil_norms = d->stencil_norms;
+    o.cc_stencil_dist = d->cc_stencil_dist; o.face_stencil_angles = d->face_stencil_angles;
+    o.point_cell_indices = d->point_cell_indices; o.point_cell_center_distances = d->point_cell_center_distances;
+    std::string err;
+    const int rc = fvdbm::mesh_properties(in, o, err);
+    if (rc == 0) return FVDBM_OK;
+    g_create_error = err;
+    return rc == -2 ? FVDBM_ERR_STATE : FVDBM_ERR_ARG;
 }
 
 // ---- host-only planning -------------------------------------------------------------------------

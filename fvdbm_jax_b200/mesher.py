@@ -80,8 +80,15 @@ class Mesher:
         b = self._canon(b).astype(np.int64)
         return np.minimum(a, b) * np.int64(self.points.shape[0]) + np.maximum(a, b)
 
-    def calc_mesh_properties(self, verbose: bool = False):
-        """Same results as reference mesher.py:319-383, computed in one vectorised sweep."""
+    def calc_mesh_properties(self, verbose: bool = False, backend: str = "native"):
+        """Same results as reference mesher.py:319-383.  ``backend="native"`` (default): the C++/OpenMP
+        Mesher-equivalent of the C-ABI library (``fvdbm_mesh_properties``, csrc/mesh.hpp; 10 M cells in about
+        a second); ``backend="numpy"``: the sort-based NumPy sweep below.  Both give bit-identical arrays
+        (tests/test_host_logic.py)."""
+        if backend == "native":
+            return self._calc_mesh_properties_native(verbose)
+        if backend != "numpy":
+            raise ValueError(f"unknown Mesher backend: {backend}")
         pts, cells, faces = self.points, self.cells, self.faces
         N, F, P = cells.shape[0], faces.shape[0], pts.shape[0]
         K = 3
@@ -218,6 +225,47 @@ class Mesher:
         if verbose:
             print(f"mesh properties: {N} cells, {F} faces, {P} points, ring width {M}")
 
+    def _calc_mesh_properties_native(self, verbose: bool = False):
+        """One call into ``fvdbm_mesh_properties`` (include/fvdbm_b200.h): outputs are allocated here with the
+        dtypes/shapes of the NumPy path and filled by the library."""
+        from . import _lib
+        lib = _lib.load()
+        pts = np.ascontiguousarray(self.points, dtype=np.float64)
+        cells = np.ascontiguousarray(self.cells, dtype=np.int32)
+        faces = np.ascontiguousarray(self.faces, dtype=np.int32)
+        if cells.ndim != 2 or cells.shape[1] != 3:
+            raise ValueError("Mesher.calc_mesh_properties handles triangles (K = 3)")
+        alias = None if self.point_alias is None else np.ascontiguousarray(self.point_alias, dtype=np.int32)
+        N, F, P = cells.shape[0], faces.shape[0], pts.shape[0]
+        M = int(lib.fvdbm_mesh_ring_width(cells.ctypes.data, None if alias is None else alias.ctypes.data, N, P))
+        if M < 0:
+            raise ValueError(_lib.last_error())
+        out = {
+            "cell_centers": np.empty((N, 2), np.float64), "cell_face_indices": np.empty((N, 3), np.int64),
+            "cell_face_normals": np.empty((N, 3, 2), np.float64), "cell_face_normal_signs": np.empty((N, 3), np.int32),
+            "faces_out": np.empty((F, 2), np.int32), "face_centers": np.empty((F, 2), np.float64),
+            "face_normals": np.empty((F, 2), np.float64), "face_lengths": np.empty(F, np.float64),
+            "face_cell_indices": np.empty((F, 2), np.int64), "face_cell_center_distances": np.empty((F, 2), np.float64),
+            "stencil_norms": np.empty((F, 2), np.float64), "cc_stencil_dist": np.empty((F, 2), np.float64),
+            "face_stencil_angles": np.empty(F, np.float64), "point_cell_indices": np.empty((P, M), np.int64),
+            "point_cell_center_distances": np.empty((P, M), np.float64),
+        }
+        d = _lib.MeshDesc()
+        d.N, d.F, d.P, d.M = N, F, P, M
+        d.points, d.cells, d.faces = pts.ctypes.data, cells.ctypes.data, faces.ctypes.data
+        d.point_alias = None if alias is None else alias.ctypes.data
+        for name, arr in out.items():
+            setattr(d, name, arr.ctypes.data)
+        rc = lib.fvdbm_mesh_properties(d)
+        if rc == _lib.ERR_STATE:
+            raise KeyError(_lib.last_error())          # the reference's dict lookup raises KeyError (mesher.py:131)
+        _lib.check(rc)
+        self.faces = out.pop("faces_out")
+        for name, arr in out.items():
+            setattr(self, name, arr)
+        if verbose:
+            print(f"mesh properties: {N} cells, {F} faces, {P} points, ring width {M}")
+
     # ------------------------------------------------------------------ to_env
     def to_env(self, dynamics, flux_method="upwind", dim_multiplier=1):
         """reference mesher.py:610-693: "upwind", "lax_wendroff" and the cell-centre-stencil variants
@@ -240,16 +288,22 @@ class Mesher:
         if cc:
             faces.alpha = np.asarray(self.face_stencil_angles, dtype=np.float64)[..., np.newaxis]
         faces.n = np.asarray(self.stencil_norms if cc else self.face_normals, dtype=np.float64)
-        faces.L = np.asarray(self.face_lengths, dtype=np.float64)[..., np.newaxis] * dim_multiplier
+        unit = dim_multiplier == 1               # x * 1 is the identity bit for bit: skip the passes over 10^7-row arrays
+        faces.L = np.asarray(self.face_lengths, dtype=np.float64)[..., np.newaxis]
+        if not unit:
+            faces.L = faces.L * dim_multiplier
         faces.nodes_index = self._canon(np.asarray(self.faces, dtype=np.int32)).astype(np.int32)
         faces.stencil_cells_index = np.asarray(self.face_cell_indices, dtype=np.int32)
-        faces.stencil_dists = np.asarray(self.cc_stencil_dist if cc else self.face_cell_center_distances,
-                                         dtype=np.float64) * dim_multiplier
+        faces.stencil_dists = np.asarray(self.cc_stencil_dist if cc else self.face_cell_center_distances, dtype=np.float64)
+        if not unit:
+            faces.stencil_dists = faces.stencil_dists * dim_multiplier
 
         nodes = Nodes(self.points.shape[0], dynamics)
         nodes.cells_index = np.asarray(self.point_cell_indices, dtype=np.int32)
-        cd = np.asarray(self.point_cell_center_distances, dtype=np.float64).copy()
-        cd[cd > 0] = cd[cd > 0] * dim_multiplier
+        cd = np.asarray(self.point_cell_center_distances, dtype=np.float64)
+        if not unit:
+            cd = cd.copy()
+            cd[cd > 0] = cd[cd > 0] * dim_multiplier
         nodes.cell_dists = cd
         nodes.type = np.zeros_like(self.point_markers[..., np.newaxis], dtype=np.int32)
         return cells, faces, nodes

@@ -224,6 +224,40 @@ int  fvdbm_halo_set_peers(fvdbm_handle* h, const int32_t* send_peers, const int6
 int  fvdbm_sfc_keys(const double* points, const int32_t* elements, int64_t ncells, int K, int bits,
                     double lo_x, double lo_y, double scale, int64_t* keys_out);
 
+/* ---- host-only Mesher-equivalent (no GPU needed; OpenMP, FVDBM_PLAN_THREADS): everything the reference's
+ * Mesher.calc_mesh_properties (/root/reference/src/mesher.py:319-383, built from :63-316 and :506-558) derives from a raw
+ * triangle mesh -- the caller-side step right before the path.  Inputs: points [P*2] f64, cells [N*3]
+ * i32 counter-clockwise (mesher.py:63-78), faces [F*2] i32, optional point_alias [P] i32 (periodic identification;
+ * NULL = none).  Every output is caller-allocated and named after the Mesher attribute it replaces; integer results
+ * are bit-identical to the reference Mesher's, floats to a few ulp of it (and bit-identical to fvdbm_jax_b200.mesher's
+ * NumPy path).  M = fvdbm_mesh_ring_width(...) sizes the two ring arrays.  Returns FVDBM_OK, FVDBM_ERR_ARG (id out of
+ * range, null pointer) or FVDBM_ERR_STATE (a cell edge is missing from `faces`: the reference raises KeyError). */
+typedef struct fvdbm_mesh_desc {
+    int64_t N, F, P;
+    int32_t M, reserved;
+    const double*  points;
+    const int32_t* cells;
+    const int32_t* faces;
+    const int32_t* point_alias;
+    double*  cell_centers;                 /* [N*2]   mesher.py:113-120 */
+    int64_t* cell_face_indices;            /* [N*3]   mesher.py:122-138 */
+    double*  cell_face_normals;            /* [N*3*2] mesher.py:140-158 (outward) */
+    int32_t* cell_face_normal_signs;       /* [N*3]   mesher.py:160-169 */
+    int32_t* faces_out;                    /* [F*2]   mesher.py:80-110 (boundary faces flipped to an outward normal) */
+    double*  face_centers;                 /* [F*2]   mesher.py:172-178 */
+    double*  face_normals;                 /* [F*2]   mesher.py:180-187 */
+    double*  face_lengths;                 /* [F]     mesher.py:189-195 */
+    int64_t* face_cell_indices;            /* [F*2]   mesher.py:197-266 (slot 0 -> slot 1 along the normal, -1 = ghost) */
+    double*  face_cell_center_distances;   /* [F*2]   mesher.py:222-283 */
+    double*  stencil_norms;                /* [F*2]   mesher.py:506-544 */
+    double*  cc_stencil_dist;              /* [F*2]   mesher.py:231-256 on the stencil direction */
+    double*  face_stencil_angles;          /* [F]     mesher.py:546-558 */
+    int64_t* point_cell_indices;           /* [P*M]   mesher.py:286-300, -1 padded */
+    double*  point_cell_center_distances;  /* [P*M]   mesher.py:302-316, -1 padded */
+} fvdbm_mesh_desc;
+int64_t fvdbm_mesh_ring_width(const int32_t* cells, const int32_t* point_alias, int64_t N, int64_t P);   /* <0: bad id */
+int  fvdbm_mesh_properties(const fvdbm_mesh_desc* mesh);
+
 /* ---- host-only planning (no GPU needed): builds the device layout from a desc so that the
  * layout logic is unit-testable on CPU.  key = name of a plan array, see csrc/plan.hpp. */
 typedef struct fvdbm_plan fvdbm_plan;

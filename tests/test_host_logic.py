@@ -128,14 +128,16 @@ def test_inconsistent_mesh_falls_back_to_staged_plan():
     hp.close()
 
 
+@pytest.mark.parametrize("backend", ["native", "numpy"])
 @pytest.mark.parametrize("name", [n for n in golden.names() if not n.startswith("quad")])
-def test_mesher_matches_reference_mesher(name):
-    """Integer connectivity bit-identical, float geometry to a few ulp (mesher.py docstring)."""
+def test_mesher_matches_reference_mesher(name, backend):
+    """Integer connectivity bit-identical, float geometry to a few ulp (mesher.py docstring); both the native
+    (fvdbm_mesh_properties, csrc/mesh.hpp) and the NumPy Mesher-equivalent against the reference Mesher's arrays."""
     case = golden.Case(name)
     g = case.g
     m = fb.Mesher()
     m.import_meshpy(case.raw())
-    m.calc_mesh_properties()
+    m.calc_mesh_properties(backend=backend)
     for key in [k[7:] for k in g.files if k.startswith("mesher.")]:
         ref, mine = g["mesher." + key], np.asarray(getattr(m, key))
         if ref.dtype.kind in "iu":
@@ -164,6 +166,105 @@ def test_mesher_matches_reference_mesher(name):
         else:
             assert np.allclose(ref, np.asarray(val).reshape(ref.shape), rtol=1e-15, atol=1e-16), key
     assert np.allclose(case.init["nodes.vel"], nodes.vel) and np.allclose(case.init["nodes.rho"], nodes.rho)
+
+
+MESHER_ARRAYS = ["cells", "faces", "cell_centers", "cell_face_indices", "cell_face_normals", "cell_face_normal_signs",
+                 "face_centers", "face_normals", "face_lengths", "face_cell_indices", "face_cell_center_distances",
+                 "stencil_norms", "cc_stencil_dist", "face_stencil_angles", "point_cell_indices", "point_cell_center_distances"]
+
+
+def _both_backends(raw):
+    out = []
+    for backend in ("numpy", "native"):
+        m = fb.Mesher()
+        m.import_meshpy(raw)
+        with np.errstate(all="ignore"):
+            m.calc_mesh_properties(backend=backend)
+        out.append(m)
+    return out
+
+
+def _assert_same_mesher_arrays(a, b):
+    for key in MESHER_ARRAYS:
+        x, y = getattr(a, key), getattr(b, key)
+        assert x.shape == y.shape and x.dtype == y.dtype, key
+        if key == "face_stencil_angles":      # libm acos vs NumPy's SIMD arccos: last bit
+            assert np.allclose(x, y, rtol=0, atol=4e-16, equal_nan=True), key
+        else:
+            assert np.array_equal(x, y, equal_nan=True), key
+
+
+def _shuffled(raw, seed):
+    """Same mesh with cells, faces and the vertices inside every cell / face in random order."""
+    rng = np.random.default_rng(seed)
+    el = np.array(raw.elements)[rng.permutation(len(raw.elements))]
+    rot = rng.integers(0, 3, el.shape[0])
+    el = np.stack([el[np.arange(el.shape[0]), (rot + k) % 3] for k in range(3)], axis=1)
+    fa = np.array(raw.faces)[rng.permutation(len(raw.faces))]
+    flip = rng.random(fa.shape[0]) < 0.5
+    fa[flip] = fa[flip][:, ::-1]
+    return types.SimpleNamespace(points=raw.points, elements=el, faces=fa, point_markers=raw.point_markers,
+                                 point_alias=getattr(raw, "point_alias", None))
+
+
+@pytest.mark.parametrize("mesh", ["square", "periodic", "cylinder", "porous", "shuffled", "shuffled_periodic"])
+def test_native_mesher_is_bitwise_the_numpy_mesher(mesh):
+    """fvdbm_mesh_properties (C++/OpenMP, CSR tables filled with atomics) == the sort-based NumPy sweep on every array,
+    for any element / face order, with and without periodic identification, independent of the thread count."""
+    raw = {"square": lambda: meshgen.triangulated_square(24, 16, seed=3),
+           "periodic": lambda: meshgen.triangulated_square(30, 20, seed=1, periodic_x=True),
+           "cylinder": lambda: meshgen.cylinder_channel(scale=1),
+           "porous": lambda: meshgen.porous_channel(scale=1.0),
+           "shuffled": lambda: _shuffled(meshgen.triangulated_square(37, 23, seed=5), 11),
+           "shuffled_periodic": lambda: _shuffled(meshgen.triangulated_square(21, 34, seed=6, periodic_x=True), 12)}[mesh]()
+    a, b = _both_backends(raw)
+    _assert_same_mesher_arrays(a, b)
+    old = os.environ.get("FVDBM_PLAN_THREADS")
+    try:
+        for nt in ("1", "3"):
+            os.environ["FVDBM_PLAN_THREADS"] = nt
+            c = fb.Mesher()
+            c.import_meshpy(raw)
+            c.calc_mesh_properties()
+            for key in MESHER_ARRAYS:
+                assert np.array_equal(getattr(b, key), getattr(c, key), equal_nan=True), (key, nt)
+    finally:
+        if old is None:
+            os.environ.pop("FVDBM_PLAN_THREADS", None)
+        else:
+            os.environ["FVDBM_PLAN_THREADS"] = old
+
+
+def test_native_mesher_edge_cases():
+    """Duplicate faces (the last one carrying a key wins, mesher.py:129), a face no cell uses, a missing face
+    (KeyError like the reference's dict lookup) and ids out of range (ValueError)."""
+    raw = meshgen.triangulated_square(6, 5, seed=2)
+    faces = np.array(raw.faces)
+    extra = np.concatenate([faces, faces[3:7][:, ::-1], np.array([[0, len(raw.points) - 1]], dtype=faces.dtype)])
+    dup = types.SimpleNamespace(points=raw.points, elements=raw.elements, faces=extra, point_markers=raw.point_markers)
+    a, b = _both_backends(dup)
+    _assert_same_mesher_arrays(a, b)
+    assert set(np.arange(len(faces), len(faces) + 4)) <= set(b.cell_face_indices.ravel())       # the duplicates won
+    assert np.array_equal(b.face_cell_indices[-1], [-1, -1]) and np.isnan(b.face_stencil_angles[-1])
+    missing = types.SimpleNamespace(points=raw.points, elements=raw.elements, faces=faces[1:], point_markers=raw.point_markers)
+    for backend in ("numpy", "native"):
+        m = fb.Mesher()
+        m.import_meshpy(missing)
+        with pytest.raises(KeyError):
+            m.calc_mesh_properties(backend=backend)
+    bad = np.array(raw.elements).copy()
+    bad[0, 0] = len(raw.points)
+    m = fb.Mesher()
+    m.points, m.cells, m.faces = np.array(raw.points, dtype=np.float64), bad.astype(np.int32), faces.astype(np.int32)
+    m.point_markers = np.array(raw.point_markers)
+    with pytest.raises(ValueError):
+        m.calc_mesh_properties()
+    with pytest.raises(ValueError):
+        fb.Mesher().calc_mesh_properties(backend="triangle")
+    empty = fb.Mesher()
+    empty.points, empty.cells, empty.faces = np.zeros((0, 2)), np.zeros((0, 3), np.int32), np.zeros((0, 2), np.int32)
+    empty.calc_mesh_properties()
+    assert empty.point_cell_indices.shape == (0, 0) and empty.cell_face_indices.shape == (0, 3)
 
 
 def test_quad_cavity_builder_equals_notebook_route():
