@@ -32,7 +32,7 @@ EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_err
            "fvdbm_set_params",
            "fvdbm_set_option", "fvdbm_info", "fvdbm_check_finite", "fvdbm_halo_set_lists", "fvdbm_halo_pack",
            "fvdbm_halo_unpack", "fvdbm_step_phase", "fvdbm_stream", "fvdbm_comm_unique_id", "fvdbm_comm_init",
-           "fvdbm_halo_set_peers", "fvdbm_sfc_keys", "fvdbm_mesh_ring_width", "fvdbm_mesh_properties", "fvdbm_plan_create",
+           "fvdbm_halo_set_peers", "fvdbm_sfc_keys", "fvdbm_mesh_ring_width", "fvdbm_mesh_properties", "fvdbm_mesh_unique_edges", "fvdbm_plan_create",
            "fvdbm_plan_destroy", "fvdbm_plan_array", "fvdbm_plan_scalar")
 
 
@@ -113,6 +113,8 @@ def load():
     lib.fvdbm_sfc_keys.restype = C.c_int
     lib.fvdbm_mesh_ring_width.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
     lib.fvdbm_mesh_ring_width.restype = C.c_int64
+    lib.fvdbm_mesh_unique_edges.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.fvdbm_mesh_unique_edges.restype = C.c_int64
     lib.fvdbm_mesh_properties.argtypes = [C.POINTER(MeshDesc)]
     lib.fvdbm_mesh_properties.restype = C.c_int
     lib.fvdbm_plan_create.argtypes = [C.POINTER(Desc), C.POINTER(P)]

@@ -57,10 +57,11 @@ class Container:
 
     def __init__(self, size, dynamics: Dynamics):
         eq = dynamics.calc_eq(np.float64(1), np.zeros(dynamics.DIM))
-        # every row = W: a read-only broadcast view (the reference's jnp arrays are immutable too; assign a new array to
-        # change it) instead of 2 GB of identical rows at 10^7 cells; consumers copy on conversion
+        # a real C-contiguous array (not np.broadcast_to: copies of a broadcast view come out Fortran-ordered), filled by
+        # broadcast assignment, which is faster than np.repeat at 10^7 rows
         eq = np.asarray(eq)
-        self.pdf = np.broadcast_to(eq, (size,) + eq.shape)
+        self.pdf = np.empty((size,) + eq.shape, dtype=eq.dtype)
+        self.pdf[...] = eq
         self.dynamics = dynamics
 
     def __repr__(self):

@@ -1109,6 +1109,13 @@ int fvdbm_mesh_properties(const fvdbm_mesh_desc* d) {
     return rc == -2 ? FVDBM_ERR_STATE : FVDBM_ERR_ARG;
 }
 
+int64_t fvdbm_mesh_unique_edges(const int32_t* cells, int64_t N, int K, int64_t P, const int32_t* point_alias, int32_t* faces_out) {
+    if (N > 0 && (!cells || !faces_out)) { g_create_error = "null argument"; return FVDBM_ERR_ARG; }
+    const int64_t f = fvdbm::mesh_unique_edges(cells, N, K, P, point_alias, faces_out);
+    if (f < 0) { g_create_error = "fvdbm_mesh_unique_edges: point id out of range, K not 3 or 4, or too many cell edges"; return FVDBM_ERR_ARG; }
+    return f;
+}
+
 // ---- host-only planning -------------------------------------------------------------------------
 int fvdbm_plan_create(const fvdbm_desc* desc, fvdbm_plan** out) {
     if (!desc || !out) { g_create_error = "null argument"; return FVDBM_ERR_ARG; }

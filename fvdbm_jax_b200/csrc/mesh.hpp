@@ -146,6 +146,57 @@ inline int64_t mesh_ring_width(const int32_t* cells, const int32_t* alias, int64
     return m;
 }
 
+// Unique undirected edges of a K-gon mesh (K = 3 or 4), one row per face, ordered by (min, max) canonical vertex id; a row
+// keeps the point ids of the FIRST half-edge (cell-major order) that produced the key -- meshgen.unique_edges' contract,
+// which np.unique(key, return_index=True) gives after an O(n log n) sort.  `faces_out` holds up to N*K rows; returns the
+// number of faces or -1 for an id out of range.
+inline int64_t mesh_unique_edges(const int32_t* cells, int64_t N, int K, int64_t P, const int32_t* alias, int32_t* faces_out) {
+    using namespace meshdetail;
+    if (N < 0 || P < 0 || K < 3 || K > 4 || N * K > INT32_MAX) return -1;
+    const int nt = threads();
+    auto canon = [alias](int64_t v) -> int64_t { return alias ? alias[v] : v; };
+    int bad = 0;
+#pragma omp parallel for num_threads(nt) schedule(static) reduction(| : bad)
+    for (int64_t s = 0; s < N * K; ++s) bad |= (cells[s] < 0 || cells[s] >= P || (alias && (alias[cells[s]] < 0 || alias[cells[s]] >= P)));
+    if (bad) return -1;
+    auto other = [&](int64_t h) -> int64_t { const int64_t c = h / K, k = h - c * K; return cells[c * K + (k + 1) % K]; };
+    std::vector<int64_t> start;
+    std::vector<int32_t> items;
+    if (!build_csr(N * K, P, [&](int64_t h) { return std::min(canon(cells[h]), canon(other(h))); }, start, items, nt)) return -1;
+    // per smaller vertex: order its half-edges by (larger vertex, half-edge id), keep the first of every run
+    std::vector<int64_t> nuniq((size_t)P + 1, 0);
+#pragma omp parallel for num_threads(nt) schedule(static, 4096)
+    for (int64_t v = 0; v < P; ++v) {
+        int32_t* a = items.data() + start[(size_t)v];
+        const int64_t n = start[(size_t)v + 1] - start[(size_t)v];
+        auto hi = [&](int32_t h) -> int64_t { return std::max(canon(cells[h]), canon(other(h))); };
+        for (int64_t i = 1; i < n; ++i) {                   // stable insertion sort by hi (segments arrive ascending in h)
+            const int32_t x = a[i];
+            const int64_t hx = hi(x);
+            int64_t j = i - 1;
+            while (j >= 0 && hi(a[j]) > hx) { a[j + 1] = a[j]; --j; }
+            a[j + 1] = x;
+        }
+        int64_t u = 0;
+        for (int64_t i = 0; i < n; ++i) if (i == 0 || hi(a[i]) != hi(a[i - 1])) ++u;
+        nuniq[(size_t)v + 1] = u;
+    }
+    for (int64_t v = 0; v < P; ++v) nuniq[(size_t)v + 1] += nuniq[(size_t)v];
+#pragma omp parallel for num_threads(nt) schedule(static, 4096)
+    for (int64_t v = 0; v < P; ++v) {
+        const int32_t* a = items.data() + start[(size_t)v];
+        const int64_t n = start[(size_t)v + 1] - start[(size_t)v];
+        int64_t w = nuniq[(size_t)v];
+        int64_t last = -1;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t h = a[i], hv = std::max(canon(cells[h]), canon(other(h)));
+            if (i == 0 || hv != last) { faces_out[2 * w] = cells[h]; faces_out[2 * w + 1] = (int32_t)other(h); ++w; }
+            last = hv;
+        }
+    }
+    return nuniq[(size_t)P];
+}
+
 // 0 ok; -1 bad argument / id out of range; -2 a cell edge is missing from `faces` (the reference raises KeyError).
 inline int mesh_properties(const MeshIn& in, MeshOut& o, std::string& err) {
     using namespace meshdetail;

@@ -182,15 +182,15 @@ class Environment:
             # CCStencilFaces (reference src/faces.py:54-72): flux * cos(alpha) == face length * cos(alpha)
             face_L = (face_L * np.cos(np.asarray(_np(f.alpha), dtype=real).reshape(-1))).astype(real)
         host = self._host
-        host["cells.pdf"] = np.array(_np(c.pdf), dtype=real).reshape(N, Q)
-        host["cells.rho"] = np.array(_np(c.rho), dtype=real).reshape(N, 1)
-        host["cells.vel"] = np.array(_np(c.vel), dtype=real).reshape(N, 2)
-        host["cells.pdf_eq"] = np.array(_np(c.pdf_eq), dtype=real).reshape(N, Q)
-        host["faces.pdf"] = np.array(_np(f.pdf), dtype=real).reshape(stencil.shape[0], Q)
+        host["cells.pdf"] = np.array(_np(c.pdf), dtype=real, order="C").reshape(N, Q)
+        host["cells.rho"] = np.array(_np(c.rho), dtype=real, order="C").reshape(N, 1)
+        host["cells.vel"] = np.array(_np(c.vel), dtype=real, order="C").reshape(N, 2)
+        host["cells.pdf_eq"] = np.array(_np(c.pdf_eq), dtype=real, order="C").reshape(N, Q)
+        host["faces.pdf"] = np.array(_np(f.pdf), dtype=real, order="C").reshape(stencil.shape[0], Q)
         Pn = _np(n.type).reshape(-1).shape[0]
-        host["nodes.pdf"] = np.array(_np(n.pdf), dtype=real).reshape(Pn, Q)
-        host["nodes.rho"] = np.array(_np(n.rho), dtype=real).reshape(Pn, 1)
-        host["nodes.vel"] = np.array(_np(n.vel), dtype=real).reshape(Pn, 2)
+        host["nodes.pdf"] = np.array(_np(n.pdf), dtype=real, order="C").reshape(Pn, Q)
+        host["nodes.rho"] = np.array(_np(n.rho), dtype=real, order="C").reshape(Pn, 1)
+        host["nodes.vel"] = np.array(_np(n.vel), dtype=real, order="C").reshape(Pn, 2)
         perm = choose_perm(self.reorder, N, getattr(c, "centers", None), stencil) if not self._n_owned else \
             (self.reorder if isinstance(self.reorder, np.ndarray) else None)
         mode = {"auto": _lib.MODE_AUTO, "fused": _lib.MODE_FUSED, "staged": _lib.MODE_STAGED}[self.mode]
@@ -316,7 +316,7 @@ class Environment:
         self._flush()
         shape = self._shape[name]
         if name.startswith("nodes."):
-            out = np.array(self._host[name], copy=True)          # untracked rows keep their values
+            out = np.array(self._host[name], copy=True, order="C")   # untracked rows keep their values
         else:
             out = np.empty(shape, dtype=self.real)
         _lib.check(self._lib.fvdbm_get(self._handle, _FIELD[name], out.ctypes.data, out.nbytes), self._handle)
@@ -450,10 +450,10 @@ class Environment:
         for view in (self.cells, self.faces, self.nodes):
             pre = {"_CellsView": "cells", "_FacesView": "faces", "_NodesView": "nodes"}[type(view).__name__]
             for k in type(view)._dynamic:
-                st[f"{pre}.{k}"] = np.array(_np(getattr(view, k)))
+                st[f"{pre}.{k}"] = np.array(_np(getattr(view, k)), order="C")
             for k in type(view)._static + getattr(type(view), "_optional", ()):
                 if k != "flux_scheme" and hasattr(view._src, k):
-                    st[f"{pre}.{k}"] = np.array(_np(getattr(view._src, k)))
+                    st[f"{pre}.{k}"] = np.array(_np(getattr(view._src, k)), order="C")
         if hasattr(c, "centers"):
             st["cells.centers"] = np.array(c.centers)
         return st

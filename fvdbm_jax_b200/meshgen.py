@@ -35,12 +35,23 @@ class RawMesh:
         return self.elements.shape[0]
 
 
-def unique_edges(elements: np.ndarray, num_points: int, alias: Optional[np.ndarray] = None) -> np.ndarray:
+def unique_edges(elements: np.ndarray, num_points: int, alias: Optional[np.ndarray] = None,
+                 backend: str = "native") -> np.ndarray:
     """Unique undirected edges of a triangulation, one row per face, sorted by (min,max) key.
 
     With ``alias`` the key is built from canonical point ids (periodic identification) while the
     returned rows keep the point ids of the first half-edge that produced the key.
     """
+    if backend == "native":                 # C++/OpenMP helper of the C-ABI library: no sort, same rows in the same order
+        from . import _lib
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        al = None if alias is None else np.ascontiguousarray(alias, dtype=np.int32)
+        out = np.empty((el.size, 2), dtype=np.int32)
+        nf = int(_lib.load().fvdbm_mesh_unique_edges(el.ctypes.data, el.shape[0], el.shape[1], int(num_points),
+                                                    None if al is None else al.ctypes.data, out.ctypes.data))
+        if nf < 0:
+            raise ValueError(_lib.last_error())
+        return out[:nf].copy()
     k = elements.shape[1]
     a = elements.reshape(-1)
     b = np.roll(elements, -1, axis=1).reshape(-1)

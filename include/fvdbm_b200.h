@@ -257,6 +257,12 @@ typedef struct fvdbm_mesh_desc {
 } fvdbm_mesh_desc;
 int64_t fvdbm_mesh_ring_width(const int32_t* cells, const int32_t* point_alias, int64_t N, int64_t P);   /* <0: bad id */
 int  fvdbm_mesh_properties(const fvdbm_mesh_desc* mesh);
+/* `faces` of a raw mesh that only has points + elements (K = 3 or 4 vertices per cell): the unique undirected edges, one
+ * row per face ordered by (min, max) canonical point id, each row carrying the point ids of the first cell edge that
+ * produced it (what the reference gets from meshpy's `mesh.faces`, /root/reference/src/mesher.py:57).  faces_out holds up
+ * to N*K rows; returns the number of faces, or FVDBM_ERR_ARG. */
+int64_t fvdbm_mesh_unique_edges(const int32_t* cells, int64_t N, int K, int64_t P, const int32_t* point_alias,
+                                int32_t* faces_out);
 
 /* ---- host-only planning (no GPU needed): builds the device layout from a desc so that the
  * layout logic is unit-testable on CPU.  key = name of a plan array, see csrc/plan.hpp. */

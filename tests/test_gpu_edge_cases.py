@@ -41,6 +41,21 @@ def mesh_problem(raw, scheme="lax_wendroff", bcs=(("vel", 1, (0.0, 0.0)), ("vel"
     return m, dyn, cells, faces, nodes
 
 
+def test_fortran_ordered_and_broadcast_inputs():
+    """Initial state handed over with non-C strides (np.array / astype keep them by default): the engine and the
+    lagged / untracked-node getters must still see the reference's row-major (elements, components) arrays."""
+    m, dyn, cells, faces, nodes = mesh_problem(meshgen.triangulated_square(7, 5, seed=4))
+    static, state = static_state(cells, faces, nodes)
+    o = StepOracle(static, state, 9, dyn.tau, dyn.delta_t, "lax_wendroff", np.float64).step(5)
+    cells.pdf = np.asfortranarray(cells.pdf)
+    nodes.pdf = np.broadcast_to(np.asarray(nodes.pdf)[0], nodes.pdf.shape)
+    nodes.vel = np.asfortranarray(nodes.vel)
+    nodes.rho = np.asfortranarray(nodes.rho)
+    env = fb.Environment(cells, faces, nodes, dtype=np.float64)
+    env.init()
+    compare(env.step(5), o, 1e-11)
+
+
 @pytest.mark.parametrize("nx,ny", [(1, 1), (2, 1), (3, 2)])
 @pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_TMA])
 def test_tiny_meshes(nx, ny, variant):

@@ -235,6 +235,23 @@ def test_native_mesher_is_bitwise_the_numpy_mesher(mesh):
             os.environ["FVDBM_PLAN_THREADS"] = old
 
 
+@pytest.mark.parametrize("periodic", [False, True])
+def test_native_unique_edges_is_the_numpy_one(periodic):
+    """fvdbm_mesh_unique_edges == np.unique-based meshgen.unique_edges: same rows, same order, point ids of the first
+    cell edge that produced a face; any cell order, triangles and quads."""
+    rng = np.random.default_rng(4)
+    raw = meshgen.triangulated_square(23, 17, seed=8, periodic_x=periodic, with_faces=False)
+    el = raw.elements[rng.permutation(raw.elements.shape[0])]
+    a = meshgen.unique_edges(el, raw.points.shape[0], raw.point_alias, backend="numpy")
+    b = meshgen.unique_edges(el, raw.points.shape[0], raw.point_alias, backend="native")
+    assert a.dtype == b.dtype and np.array_equal(a, b)
+    quads = np.array([[0, 1, 4, 3], [1, 2, 5, 4], [3, 4, 7, 6], [4, 5, 8, 7]], dtype=np.int32)
+    assert np.array_equal(meshgen.unique_edges(quads, 9, backend="numpy"), meshgen.unique_edges(quads, 9, backend="native"))
+    assert meshgen.unique_edges(np.zeros((0, 3), np.int32), 5).shape == (0, 2)
+    with pytest.raises(ValueError):
+        meshgen.unique_edges(np.array([[0, 1, 7]], dtype=np.int32), 5)
+
+
 def test_native_mesher_edge_cases():
     """Duplicate faces (the last one carrying a key wins, mesher.py:129), a face no cell uses, a missing face
     (KeyError like the reference's dict lookup) and ids out of range (ValueError)."""
@@ -309,6 +326,30 @@ def test_environment_surface_without_gpu(tmp_path):
     path = m.to_vtk(env, str(tmp_path / "out"), save_f=True)
     txt = open(path).read()
     assert "UNSTRUCTURED_GRID" in txt and "VECTORS Velocity double" in txt and f"CELLS 100 400" in txt and "pdf 9 100 double" in txt
+
+
+def test_host_state_is_c_ordered_whatever_the_input_strides():
+    """Fortran-ordered or broadcast inputs (np.array / astype keep such strides by default) must not reach the raw
+    pointers of the C ABI: the host copies Environment hands to fvdbm_create / fvdbm_get are C-contiguous."""
+    m = fb.Mesher()
+    m.import_meshpy(meshgen.triangulated_square(3, 2, jitter=0.0))
+    m.calc_mesh_properties()
+    dyn = fb.D2Q9(0.8, 0.1)
+    cells, faces, nodes = m.to_env(dyn, "lax_wendroff")
+    for cont in (cells, faces, nodes):         # fresh containers: real, writable, C-ordered arrays
+        assert cont.pdf.flags.c_contiguous and cont.pdf.flags.writeable
+    ref = {"cells.pdf": np.array(cells.pdf), "nodes.pdf": np.array(nodes.pdf)}
+    cells.pdf = np.asfortranarray(cells.pdf)
+    nodes.pdf = np.broadcast_to(np.asarray(nodes.pdf)[0], nodes.pdf.shape)
+    nodes.vel = np.asfortranarray(nodes.vel)
+    env = fb.Environment(cells, faces, nodes, dtype=np.float32)
+    env.init()
+    da = env._describe()
+    for name, arr in env._host.items():
+        assert arr.flags.c_contiguous, name
+    for name in ref:
+        assert np.array_equal(env._host[name], ref[name].astype(np.float32)), name
+    assert all(a.flags.c_contiguous for a in da.keep.values() if isinstance(a, np.ndarray))
 
 
 def test_custom_array_semantics():
