@@ -1,8 +1,11 @@
 """Legacy-VTK export without pyvista (reference Mesher.to_vtk, /root/reference/src/mesher.py:562-598).
 
-Writes an ASCII "# vtk DataFile Version 3.0" UNSTRUCTURED_GRID with the same cell data the
-reference attaches: ``Velocity`` (3-vector, z = 0), ``Density`` and optionally ``pdf`` / ``feq``.
-Any VTK reader (ParaView, pyvista.read) opens it."""
+Writes a "# vtk DataFile Version 3.0" UNSTRUCTURED_GRID with the same cell data the reference
+attaches: ``Velocity`` (3-vector, z = 0), ``Density`` and optionally ``pdf`` / ``feq``.  Any VTK
+reader (ParaView, pyvista.read) opens it.  ``binary=True`` writes the BINARY flavour (big-endian
+raw arrays, what pyvista's ``grid.save`` produces by default): one ``tofile`` per array instead of
+one formatted number at a time, minutes -> seconds at 10^7 cells.  ``binary=None`` (default) picks
+BINARY from 100 000 cells up and ASCII (human-readable) below."""
 from __future__ import annotations
 
 import numpy as np
@@ -10,13 +13,51 @@ import numpy as np
 VTK_TRIANGLE, VTK_QUAD = 5, 9
 
 
-def write_vtk(mesher, env, filename: str, save_f: bool = False, save_feq: bool = False) -> str:
+def _write_binary(path, pts, cells, vel, rho, extra):
+    n, k = cells.shape
+
+    def be(a, dt):
+        return np.ascontiguousarray(a, dtype=np.dtype(dt).newbyteorder(">"))
+
+    with open(path, "wb") as f:
+        f.write(b"# vtk DataFile Version 3.0\nfvdbm_jax_b200 export\nBINARY\nDATASET UNSTRUCTURED_GRID\n")
+        f.write(f"POINTS {pts.shape[0]} double\n".encode())
+        be(np.hstack([pts, np.zeros((pts.shape[0], 1))]), "f8").tofile(f)
+        f.write(f"\nCELLS {n} {n * (k + 1)}\n".encode())
+        be(np.hstack([np.full((n, 1), k, dtype=np.int64), cells]), "i4").tofile(f)
+        f.write(f"\nCELL_TYPES {n}\n".encode())
+        be(np.full(n, VTK_TRIANGLE if k == 3 else VTK_QUAD), "i4").tofile(f)
+        f.write(f"\nCELL_DATA {n}\nVECTORS Velocity double\n".encode())
+        be(np.hstack([vel[:, :2], np.zeros((n, 1))]), "f8").tofile(f)
+        f.write(b"\nSCALARS Density double 1\nLOOKUP_TABLE default\n")
+        be(rho, "f8").tofile(f)
+        if extra:
+            f.write(f"\nFIELD FieldData {len(extra)}\n".encode())
+            for name, arr in extra:
+                f.write(f"{name} {arr.shape[1]} {n} double\n".encode())
+                be(arr, "f8").tofile(f)
+                f.write(b"\n")
+        else:
+            f.write(b"\n")
+    return path
+
+
+def write_vtk(mesher, env, filename: str, save_f: bool = False, save_feq: bool = False, binary=None) -> str:
     pts = np.asarray(mesher.points, dtype=np.float64)
     cells = np.asarray(mesher.cells, dtype=np.int64)
     n, k = cells.shape
     vel = np.asarray(env.cells.vel, dtype=np.float64).reshape(n, -1)
     rho = np.asarray(env.cells.rho, dtype=np.float64).reshape(n)
     path = f"{filename}.vtk"
+    if binary is None:
+        binary = n >= 100_000
+    if binary:
+        extra = []
+        if save_f:
+            extra.append(("pdf", np.asarray(env.cells.pdf, dtype=np.float64)))
+        if save_feq:
+            extra.append(("feq", np.asarray(env.cells.pdf_eq, dtype=np.float64)))
+        return _write_binary(path, pts, cells, vel, rho, extra)
     with open(path, "w") as f:
         f.write("# vtk DataFile Version 3.0\nfvdbm_jax_b200 export\nASCII\nDATASET UNSTRUCTURED_GRID\n")
         f.write(f"POINTS {pts.shape[0]} double\n")

@@ -356,10 +356,10 @@ class Mesher:
                                centers=self.cell_centers, method=method, refine=refine)
 
     # ------------------------------------------------------------------ export
-    def to_vtk(self, env: Environment, filename: str, save_f: bool = False, save_feq: bool = False):
+    def to_vtk(self, env: Environment, filename: str, save_f: bool = False, save_feq: bool = False, binary=None):
         """Legacy-VTK writer with the cell data of reference mesher.py:562-598 (no pyvista)."""
         from .export import write_vtk
-        return write_vtk(self, env, filename, save_f, save_feq)
+        return write_vtk(self, env, filename, save_f, save_feq, binary)
 
     def to_pickle(self, env: Environment, filename: str):
         with open(f"{filename}.pkl", "wb") as f:

@@ -328,6 +328,66 @@ def test_environment_surface_without_gpu(tmp_path):
     assert "UNSTRUCTURED_GRID" in txt and "VECTORS Velocity double" in txt and f"CELLS 100 400" in txt and "pdf 9 100 double" in txt
 
 
+def _read_legacy_vtk_binary(path):
+    """Minimal reader of the BINARY legacy format (big-endian raw arrays after each header line)."""
+    raw = open(path, "rb").read()
+    pos = 0
+    out = {}
+
+    def line():
+        nonlocal pos
+        while raw[pos:pos + 1] == b"\n":
+            pos += 1
+        end = raw.index(b"\n", pos)
+        text = raw[pos:end].decode()
+        pos = end + 1
+        return text
+
+    def arr(dt, count):
+        nonlocal pos
+        a = np.frombuffer(raw, dtype=np.dtype(dt).newbyteorder(">"), count=count, offset=pos)
+        pos += a.nbytes
+        return a
+
+    assert line().startswith("# vtk DataFile Version")
+    line()
+    assert line() == "BINARY" and line() == "DATASET UNSTRUCTURED_GRID"
+    npts = int(line().split()[1])
+    out["points"] = arr("f8", 3 * npts).reshape(npts, 3)
+    _, n, tot = line().split()
+    out["cells"] = arr("i4", int(tot)).reshape(int(n), -1)
+    assert line() == f"CELL_TYPES {n}"
+    out["types"] = arr("i4", int(n))
+    assert line() == f"CELL_DATA {n}" and line() == "VECTORS Velocity double"
+    out["Velocity"] = arr("f8", 3 * int(n)).reshape(int(n), 3)
+    assert line() == "SCALARS Density double 1" and line() == "LOOKUP_TABLE default"
+    out["Density"] = arr("f8", int(n))
+    nf = int(line().split()[2])
+    for _ in range(nf):
+        name, comps, tuples, _ = line().split()
+        out[name] = arr("f8", int(comps) * int(tuples)).reshape(int(tuples), int(comps))
+    return out
+
+
+def test_binary_vtk_round_trip(tmp_path):
+    """to_vtk(binary=True): the BINARY legacy file pyvista's grid.save writes by default (reference mesher.py:562-598),
+    read back array by array."""
+    case = golden.Case("channel_lw")
+    cells, faces, nodes = case.containers()
+    env = fb.Environment(cells, faces, nodes)
+    env.init()
+    m = fb.Mesher()
+    m.import_meshpy(case.raw())
+    m.calc_mesh_properties()
+    got = _read_legacy_vtk_binary(m.to_vtk(env, str(tmp_path / "bin"), save_f=True, save_feq=True, binary=True))
+    assert np.array_equal(got["points"][:, :2], m.points) and not got["points"][:, 2].any()
+    assert np.array_equal(got["cells"][:, 1:], m.cells) and (got["cells"][:, 0] == 3).all() and (got["types"] == 5).all()
+    assert np.array_equal(got["Velocity"][:, :2], np.asarray(env.cells.vel)) and np.array_equal(got["Density"], np.asarray(env.cells.rho).ravel())
+    assert np.array_equal(got["pdf"], np.asarray(env.cells.pdf)) and np.array_equal(got["feq"], np.asarray(env.cells.pdf_eq))
+    txt = open(m.to_vtk(env, str(tmp_path / "auto"))).read()         # 100 cells: ASCII by default
+    assert "ASCII" in txt
+
+
 def test_host_state_is_c_ordered_whatever_the_input_strides():
     """Fortran-ordered or broadcast inputs (np.array / astype keep such strides by default) must not reach the raw
     pointers of the C ABI: the host copies Environment hands to fvdbm_create / fvdbm_get are C-contiguous."""
