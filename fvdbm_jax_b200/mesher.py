@@ -266,6 +266,67 @@ class Mesher:
         if verbose:
             print(f"mesh properties: {N} cells, {F} faces, {P} points, ring width {M}")
 
+    # ------------------------------------------------------- mesh quality report
+    def verify_stencil_geometry(self, verbose: bool = True):
+        """Mesh-quality report of reference mesher.py:386-504 over the interior faces, vectorised: angle between
+        the centre-to-centre vector and the face normal, projected-distance error, face-centre offset, and the
+        face-normal vs stencil-normal projected distances.  Prints the reference's lines (``verbose``) and returns
+        the statistics as a dict (an extension; the reference returns None)."""
+        fci = np.asarray(self.face_cell_indices)
+        inner = (fci[:, 0] != -1) & (fci[:, 1] != -1)
+        c0, c1 = self.cell_centers[fci[inner, 0]], self.cell_centers[fci[inner, 1]]
+        n = self.face_normals[inner]
+        L = self.face_lengths[inner]
+        dists = self.face_cell_center_distances[inner]
+        nrm = lambda a: np.sqrt(a[:, 0] * a[:, 0] + a[:, 1] * a[:, 1])          # noqa: E731
+        pct = lambda a: np.where(L > 0, 100.0 * a / np.where(L > 0, L, 1.0), 0.0)  # noqa: E731
+        v = c1 - c0
+        n_norm = n / nrm(n)[:, None]
+        angles = np.degrees(np.arccos(np.clip(_dot(v / nrm(v)[:, None], n_norm), -1, 1)))
+        dist_err = np.abs(_dot(v, n_norm) - (dists[:, 0] + dists[:, 1]))
+        midpoint = (c0 + c1) / 2.0
+        offsets = nrm(self.face_centers[inner] - midpoint)
+        centre_vs_face = pct(nrm(v) - (np.abs(dists[:, 0]) + np.abs(dists[:, 1])))
+        sn = self.stencil_norms[inner]
+        s_norm = sn / nrm(sn)[:, None]
+        proj = [(_dot(n_norm, c - midpoint), _dot(s_norm, c - midpoint)) for c in (c0, c1)]
+        diffs = np.stack([np.abs(f - t) for f, t in proj], axis=1)              # (faces, [d0, d1]) like the reference's extend
+        pdiffs = np.stack([pct(d) for d in diffs.T], axis=1)
+        mismatches = int(sum(np.count_nonzero(np.sign(f) != np.sign(t)) for f, t in proj))
+        mean = lambda a: float(np.mean(a)) if a.size else float("nan")          # noqa: E731
+        amax = lambda a: float(np.max(a)) if a.size else float("nan")           # noqa: E731
+        amin = lambda a: float(np.min(a)) if a.size else float("nan")           # noqa: E731
+        r = {"interior_faces": int(inner.sum()),
+             "angle_mean_deg": mean(angles), "angle_max_deg": amax(angles), "bad_angle_faces": int(np.count_nonzero(np.abs(angles) > 30)),
+             "distance_error_mean": mean(dist_err), "distance_error_max": amax(dist_err),
+             "distance_error_pct_mean": mean(pct(dist_err)), "distance_error_pct_max": amax(pct(dist_err)),
+             "bad_distance_faces": int(np.count_nonzero(pct(dist_err) > 1.0)),
+             "offset_mean": mean(offsets), "offset_max": amax(offsets), "offset_pct_mean": mean(pct(offsets)),
+             "offset_pct_max": amax(pct(offsets)), "bad_offset_faces": int(np.count_nonzero(pct(offsets) > 10.0)),
+             "centre_vs_face_pct_mean": mean(centre_vs_face), "centre_vs_face_pct_max": amax(centre_vs_face),
+             "centre_vs_face_pct_min": amin(centre_vs_face),
+             "stencil_diff_mean": mean(diffs), "stencil_diff_max": amax(diffs), "stencil_diff_pct_mean": mean(pdiffs),
+             "stencil_diff_pct_max": amax(pdiffs), "stencil_large_diffs": int(np.count_nonzero(pdiffs > 1.0)),
+             "stencil_sign_mismatches": mismatches}
+        if verbose:
+            print(f"Mean angle (deg): {r['angle_mean_deg']:.2f}, max: {r['angle_max_deg']:.2f}")
+            print(f"Faces with angle > 30 deg: {r['bad_angle_faces']}")
+            print(f"Mean distance error: {r['distance_error_mean']:.4f}, max: {r['distance_error_max']:.4f}")
+            print(f"Mean distance error (% of face length): {r['distance_error_pct_mean']:.2f}%, max: {r['distance_error_pct_max']:.2f}%")
+            print(f"Faces with distance error > 1% of face length: {r['bad_distance_faces']}")
+            print(f"Mean face center offset: {r['offset_mean']:.4e}, max: {r['offset_max']:.4e}")
+            print(f"Mean face center offset (% of face length): {r['offset_pct_mean']:.2f}%, max: {r['offset_pct_max']:.2f}%")
+            print(f"Faces with face center offset > 10% of face length: {r['bad_offset_faces']}")
+            print(f"Mean (cell center dist - face dist sum) as % of face length: {r['centre_vs_face_pct_mean']:.4e}%, "
+                  f"max: {r['centre_vs_face_pct_max']:.4e}%, min: {r['centre_vs_face_pct_min']:.4e}%")
+            print("\nStencil distance checks:")
+            print(f"Mean |face-normal dist - stencil-normal dist|: {r['stencil_diff_mean']:.4e}, max: {r['stencil_diff_max']:.4e}")
+            print(f"Mean |face-normal dist - stencil-normal dist| (% of face length): {r['stencil_diff_pct_mean']:.2f}%, "
+                  f"max: {r['stencil_diff_pct_max']:.2f}%")
+            print(f"Faces with |face-normal dist - stencil-normal dist| > 1.0%: {r['stencil_large_diffs']}")
+            print(f"Faces with sign mismatch between face-normal and stencil-normal projected distances: {r['stencil_sign_mismatches']}")
+        return r
+
     # ------------------------------------------------------------------ to_env
     def to_env(self, dynamics, flux_method="upwind", dim_multiplier=1):
         """reference mesher.py:610-693: "upwind", "lax_wendroff" and the cell-centre-stencil variants

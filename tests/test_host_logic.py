@@ -388,6 +388,21 @@ def test_binary_vtk_round_trip(tmp_path):
     assert "ASCII" in txt
 
 
+def test_stencil_geometry_report(capsys):
+    """verify_stencil_geometry (reference mesher.py:386-504; pinned to the reference's printout in
+    tests/test_reference_containers.py): on an unjittered grid the face-normal projections are exact, the diagonal
+    faces' centres sit on the centre-to-centre midpoint and the report has the reference's 14 lines."""
+    m = fb.Mesher()
+    m.import_meshpy(meshgen.triangulated_square(6, 4, jitter=0.0))
+    m.calc_mesh_properties()
+    r = m.verify_stencil_geometry()
+    out = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip()]
+    assert len(out) == 14 and out[0].startswith("Mean angle (deg):") and out[-1].startswith("Faces with sign mismatch")
+    assert r["interior_faces"] == int(((m.face_cell_indices != -1).all(axis=1)).sum())
+    assert r["distance_error_max"] < 1e-12 and r["bad_distance_faces"] == 0 and r["bad_angle_faces"] == 0
+    assert m.verify_stencil_geometry(verbose=False) == r and capsys.readouterr().out == ""
+
+
 def test_host_state_is_c_ordered_whatever_the_input_strides():
     """Fortran-ordered or broadcast inputs (np.array / astype keep such strides by default) must not reach the raw
     pointers of the C ABI: the host copies Environment hands to fvdbm_create / fvdbm_get are C-contiguous."""

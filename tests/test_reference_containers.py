@@ -57,3 +57,26 @@ def test_reference_create_route_with_custom_arrays_is_accepted():
     assert da.keep["face_cell_idx"].tolist()[3] == [0, -1] and da.keep["node_cell_idx"].shape == (6, 1)
     hp = fb._lib.HostPlan(da)
     assert hp.scalar("fused_ok") == 1 and hp.scalar("NB") == 6
+
+
+def test_stencil_geometry_report_equals_the_reference_printout(capsys):
+    """Mesher.verify_stencil_geometry (reference mesher.py:386-504): same numbers in the report, line by line (the
+    lines carry 2-4 significant digits; lines whose value is rounding noise around zero are compared as numbers)."""
+    import re
+    import fvdbm_jax_b200 as fb
+    case = golden.Case("cylinder_lw")
+    ref = refrun.ref_mesher(case.raw())
+    capsys.readouterr()
+    ref.verify_stencil_geometry()
+    want = capsys.readouterr().out.strip().splitlines()
+    m = fb.Mesher()
+    m.import_meshpy(case.raw())
+    m.calc_mesh_properties()
+    stats = m.verify_stencil_geometry()
+    got = capsys.readouterr().out.strip().splitlines()
+    assert len(want) == len(got) >= 14 and stats["interior_faces"] > 0
+    num = re.compile(r"[-+]?\d+\.?\d*(?:e[-+]?\d+)?")
+    for a, b in zip(want, got):
+        assert num.sub("#", a) == num.sub("#", b)                   # same text
+        for x, y in zip(num.findall(a), num.findall(b)):
+            assert abs(float(x) - float(y)) <= 1e-9 + 2e-3 * abs(float(x)), (a, b)
