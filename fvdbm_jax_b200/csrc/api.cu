@@ -297,7 +297,9 @@ struct EngineT final : Engine {
         if (const char* e = getenv("FVDBM_TILE_CELLS")) tile_cells = atoi(e);
         if (const char* e = getenv("FVDBM_STAGES")) stages = atoi(e);
         // latency-bound meshes: batch iterations in CUDA graphs by default (20k cells: 13.2 -> 7.2 us/step)
-        if (plan.No < 1000000) { graph_steps = 50; pdl = 1; }      // (at 2M cells graphs measured slightly slower: 70.9 vs 65.5 us)
+        // PDL chain + graphs win up to ~1M cells (1.0M: 25.1 vs 26.6 us per iteration), the two-stream schedule from 2M
+        // (43.0 vs 44.9 us); profiles/r2_schedule_sweep_rec256.jsonl
+        if (plan.No < 1500000) { graph_steps = 50; pdl = 1; }
         if (const char* e = getenv("FVDBM_PDL")) pdl = atoi(e) ? 1 : 0;
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
@@ -308,16 +310,17 @@ struct EngineT final : Engine {
     }
     size_t max_smem = 0;
     int occ_cache = 0;
-    // fp32 D2Q9: the record-layout kernel (single-sector 128-bit gathers, FFMA2 over population pairs) where it
-    // measured fastest -- the bandwidth-bound regime (>= 4M owned cells: 0.2257 vs 0.2309 (direct) / 0.2362 (pair) ms
-    // sustained per 10M-cell iteration on one box) and very small meshes (<= 64k cells: 5.3-5.6 vs 5.7-6.0 us/step);
-    // in between the thread-per-cell AoSoA kernel is as fast or faster (2M-cell porous: 51.0 vs 52.5 us).
-    // fp32 D2Q13 >= 4M cells: the packed two-cells-per-thread kernel.  fp64: thread-per-cell AoSoA (the fp64 record
-    // is 64 B and its strided 128-bit accesses lose: 0.518 vs 0.359 ms).   profiles/r2_ab_record_kernel.jsonl
+    // fp32 D2Q9: the record-layout kernel (one 256-bit access per record, FFMA2 over population pairs) at every size: with
+    // 256-bit accesses it is as fast as or faster than the thread-per-cell AoSoA kernel from 10k to 10M cells (20k: 4.88 vs
+    // 5.05 us, cylinder 194k: 8.50 vs 9.11, 500k: 12.3 vs 13.2, 1M: 24.6 vs 26.7, porous 2M: 49.2 vs 50.9, 4M: 81.3 vs 81.0,
+    // 10M sustained: 0.204 vs 0.228 ms; only 50k-100k squares are 1-2 % behind) -- profiles/r2_variant_crossover.jsonl,
+    // r2_small_configs_rec256.jsonl, r2_ab_record_kernel.jsonl.  fp32 D2Q13: thread-per-cell over records up to 64k cells
+    // (5.57 vs 5.82 us), the packed two-cells-per-thread kernel from 4M.  fp64: thread-per-cell AoSoA (the fp64 record is
+    // 64 B and its strided 128-bit accesses lose: 0.518 vs 0.359 ms).
     int default_variant() const {
         if (sizeof(real) == 4 && mode == FVDBM_MODE_FUSED) {
             const bool big = plan.No >= (int64_t(1) << 22), small = plan.No <= (int64_t(1) << 16);
-            if ((Q == 9 && big) || small) return FVDBM_VARIANT_REC;      // (D2Q13 <= 64k: thread-per-cell over records, 5.63 vs 6.01 us)
+            if (Q == 9 || small) return FVDBM_VARIANT_REC;
             if (big) return FVDBM_VARIANT_PAIR;
         }
         return FVDBM_VARIANT_DIRECT;

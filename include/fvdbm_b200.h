@@ -56,17 +56,17 @@ extern "C" {
 #define FVDBM_MODE_FUSED  2   /* node kernel + one cell-centric kernel per step                   */
 
 /* fused-kernel variants (fvdbm_set_option(h, FVDBM_OPT_VARIANT, v)) */
-#define FVDBM_VARIANT_AUTO   0   /* fp32: REC for D2Q9 with >= 4M owned cells and for any lattice with <= 64k;
-                                    PAIR for D2Q13 >= 4M; otherwise (and fp64) DIRECT -- measured choices,
-                                    api.cu: default_variant                                                   */
+#define FVDBM_VARIANT_AUTO   0   /* fp32: REC for D2Q9 (every size) and for D2Q13 with <= 64k owned cells; PAIR
+                                    for D2Q13 >= 4M; otherwise (and fp64) DIRECT -- measured choices, api.cu:
+                                    default_variant                                                           */
 #define FVDBM_VARIANT_DIRECT 1   /* thread per cell, all operands through L1/L2               */
 #define FVDBM_VARIANT_TMA    2   /* persistent CTAs, cp.async.bulk + mbarrier tile pipeline   */
 #define FVDBM_VARIANT_PAIR   3   /* fp32 only: two cells per thread, packed FFMA2 math, 64-bit
                                     coalesced streaming accesses                              */
 #define FVDBM_VARIANT_REC    4   /* thread per cell over the RECORD layout (a cell's Q-1 moving populations are
                                     contiguous -- one 32-byte sector for fp32 D2Q9 -- so a neighbour gather is
-                                    a few 128-bit loads from one or two sectors); fp32 D2Q9 additionally packs
-                                    the arithmetic over population pairs (FFMA2)                              */
+                                    one 256-bit load of one sector, a few 128-bit loads otherwise); fp32 D2Q9
+                                    additionally packs the arithmetic over population pairs (FFMA2)                              */
 /* All variants execute the same canonical operation sequence: results are bit-identical.
  * Debug / A-B environment overrides read once at fvdbm_create (each mirrors an fvdbm_option):
  *   FVDBM_VARIANT, FVDBM_TILE_CELLS, FVDBM_STAGES, FVDBM_GRAPH_STEPS, FVDBM_CTAS_PER_SM,

@@ -301,7 +301,7 @@ def test_full_size_properties():
     rho_lag = env.cells.rho.copy()
     prev = np.empty((n, 9), np.float32)
     env.get_into("cells.pdf", prev)                     # current
-    assert env.info(_lib.INFO_VARIANT) == (_lib.VARIANT_REC if (n >= 1 << 22 or n <= 1 << 16) else _lib.VARIANT_DIRECT)   # default kernel produced `a`
+    assert env.info(_lib.INFO_VARIANT) == _lib.VARIANT_REC      # default kernel (fp32 D2Q9: records at every size) produced `a`
     for variant, reverse in ((_lib.VARIANT_TMA, 0), (_lib.VARIANT_DIRECT, 1), (_lib.VARIANT_PAIR, 1), (_lib.VARIANT_REC, 0)):
         env.set_option(_lib.OPT_VARIANT, variant).set_option(_lib.OPT_REVERSE_SWEEP, reverse)
         assert env.info(_lib.INFO_VARIANT) == variant
