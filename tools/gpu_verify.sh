@@ -16,4 +16,6 @@ echo "ncu full rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))s"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --inner 5 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))s"
+timeout 150 python tools/configs_bench.py > gpurun_out/small_configs.jsonl 2> gpurun_out/small_configs.err
+echo "small configs rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))s"; cut -c1-220 gpurun_out/small_configs.jsonl
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
