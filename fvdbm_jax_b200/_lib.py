@@ -25,7 +25,7 @@ VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA, VARIANT_PAIR, VARIANT_REC = 0, 1, 2, 
 (INFO_MODE, INFO_STEPS, INFO_LAUNCHES, INFO_TRACKED_NODES, INFO_BOUNDARY_SIDES, INFO_DEVICE_BYTES,
  INFO_VARIANT, INFO_NPAD, INFO_FUSED_OK, INFO_HALO_CELLS, INFO_OWNED_CELLS, INFO_GRAPH_STEPS) = range(12)
 (OPT_VARIANT, OPT_TILE_CELLS, OPT_STAGES, OPT_GRAPH_STEPS, OPT_CTAS_PER_SM, OPT_REVERSE_SWEEP,
- OPT_TEMPORAL, OPT_PREFETCH_DIST, OPT_PDL, OPT_FUSE_NODES) = range(10)
+ OPT_TEMPORAL, OPT_PREFETCH_DIST, OPT_PDL) = range(9)
 
 EXPORTS = ("fvdbm_abi_version", "fvdbm_create", "fvdbm_destroy", "fvdbm_last_error", "fvdbm_step",
            "fvdbm_step_timed", "fvdbm_sync", "fvdbm_get", "fvdbm_set", "fvdbm_set_async", "fvdbm_get_async", "fvdbm_wait",

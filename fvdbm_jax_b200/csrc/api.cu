@@ -183,9 +183,6 @@ struct EngineT final : Engine {
     int64_t tickets = 0;
     DevBuf<int32_t> halo_send, halo_recv;
     DevBuf<unsigned long long> counter;
-    DevBuf<unsigned> stepsync;           // k_step_rec: {done, finished, error}
-    int fuse_nodes = 1;                  // single-kernel iteration where it applies (step_in_one_launch())
-    bool step_sync_used = false;
     // native exchange (optional)
     ncclComm_t comm = nullptr;
     std::vector<int> send_peers, recv_peers;
@@ -275,8 +272,6 @@ struct EngineT final : Engine {
         CU_TRY(npdf.upload(plan.tn_pdf, stream));
         CU_TRY(nrho.upload(plan.tn_rho, stream));
         CU_TRY(nvel.upload(plan.tn_vel, stream));
-        CU_TRY(stepsync.alloc(4));
-        CU_TRY(cudaMemsetAsync(stepsync.p, 0, 4 * sizeof(unsigned), stream));
         CU_TRY(s_cface.upload(plan.s_cface, stream));
         CU_TRY(s_csign.upload(plan.s_csign, stream));
         CU_TRY(s_fcell.upload(plan.s_fcell, stream));
@@ -306,7 +301,6 @@ struct EngineT final : Engine {
         // (43.0 vs 44.9 us); profiles/r2_schedule_sweep_rec256.jsonl
         if (plan.No < 1500000) { graph_steps = 50; pdl = 1; }
         if (const char* e = getenv("FVDBM_PDL")) pdl = atoi(e) ? 1 : 0;
-        if (const char* e = getenv("FVDBM_FUSE_NODES")) fuse_nodes = atoi(e) ? 1 : 0;
         if (const char* e = getenv("FVDBM_GRAPH_STEPS")) graph_steps = atoi(e);
         if (const char* e = getenv("FVDBM_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char* e = getenv("FVDBM_REVERSE_SWEEP")) reverse_sweep = atoi(e);
@@ -499,33 +493,12 @@ struct EngineT final : Engine {
     // dependent on the previous one (PDL) so launch latency and the kernels' prologues (index math, streaming loads)
     // overlap the predecessor's tail.  Bandwidth-bound meshes keep the two-stream overlap schedule below.
     bool pdl_chain() const { return pdl && mode == FVDBM_MODE_FUSED && !native_exchange() && plan.No == plan.N && !phase0_done; }
-    // ... and for fp32 D2Q9 over records the chain is ONE launch per iteration: node CTAs + cell CTAs (kernels.cuh: k_step_rec)
-    bool step_in_one_launch() const {
-        return fuse_nodes && pdl_chain() && variant == FVDBM_VARIANT_REC && Q == 9 && sizeof(real) == 4 && owned_end() > 0;
-    }
-    int launch_step(const FusedArgs<float>& a, const NodeArgs<float>& na) {
-        if constexpr (Q == 9 && sizeof(real) == 4) {
-            const unsigned node_blocks = blocks_for((int64_t)plan.NA * kNodeLanes, FVDBM_REC_THREADS);
-            const unsigned cell_blocks = blocks_for(a.cell_end - a.cell_begin, FVDBM_REC_THREADS);
-            StepSync sy{stepsync.p, stepsync.p + 1, stepsync.p + 2};
-            CU_TRY(launch_k(k_step_rec<K, SCHEME>, node_blocks + cell_blocks, FVDBM_REC_THREADS, 0, stream, true, a, na, (int)node_blocks, sy));
-            ++launches;
-            step_sync_used = true;
-            CU_TRY(cudaGetLastError());
-        }
-        return FVDBM_OK;
-    }
-    int launch_step(const FusedArgs<double>&, const NodeArgs<double>&) { return FVDBM_OK; }
 
     int step_fused_once() {
         int rc;
         if (pdl_chain()) {
-            if (step_in_one_launch()) {
-                if ((rc = launch_step(fused_args(0, owned_end()), node_args(plan.NA)))) return rc;
-            } else {
-                if ((rc = launch_nodes())) return rc;
-                if ((rc = launch_fused(0, owned_end(), stream))) return rc;
-            }
+            if ((rc = launch_nodes())) return rc;
+            if ((rc = launch_fused(0, owned_end(), stream))) return rc;
             prev = cur; cur = nxt(); ++steps;
             return FVDBM_OK;
         }
@@ -661,7 +634,6 @@ struct EngineT final : Engine {
     int64_t launches_per_step() const {
         if (mode == FVDBM_MODE_STAGED) return 3 + (plan.NA > 0 ? 1 : 0);
         // own kernels only: the grouped ncclSend/Recv of a native exchange is NCCL's launch, not counted
-        if (step_in_one_launch()) return 1;
         if (pdl_chain()) return (plan.NA > 0 ? 1 : 0) + 1;
         return (plan.NA > 0 ? 1 : 0) + (plan.Bstart > 0 ? 1 : 0) + (owned_end() > plan.Bstart ? 1 : 0) +
                (native_exchange() ? (halo_send.n ? 1 : 0) + (halo_recv.n ? 1 : 0) : 0);
@@ -690,11 +662,6 @@ struct EngineT final : Engine {
         CU_TRY(cudaStreamSynchronize(stream));
         CU_TRY(cudaStreamSynchronize(xout));
         CU_TRY(cudaGetLastError());
-        if (step_sync_used) {              // k_step_rec: a bounded wait that gave up (never in a correct run)
-            unsigned flag = 0;
-            CU_TRY(cudaMemcpy(&flag, stepsync.p + 2, sizeof(flag), cudaMemcpyDeviceToHost));
-            if (flag) { err = "k_step_rec: a border CTA timed out waiting for the boundary-node CTAs"; return FVDBM_ERR_STATE; }
-        }
         return FVDBM_OK;
     }
 
@@ -889,7 +856,6 @@ struct EngineT final : Engine {
         case FVDBM_OPT_CTAS_PER_SM: ctas_per_sm = (int)v; break;
         case FVDBM_OPT_REVERSE_SWEEP: reverse_sweep = v ? 1 : 0; break;
         case FVDBM_OPT_PDL: pdl = v ? 1 : 0; break;
-        case FVDBM_OPT_FUSE_NODES: fuse_nodes = v ? 1 : 0; break;
         case FVDBM_OPT_PREFETCH_DIST: if (v < 0 || v > (1 << 20)) { err = "prefetch distance out of range"; return FVDBM_ERR_ARG; } prefetch_dist = (int)v; break;
         case FVDBM_OPT_TEMPORAL:
             if (v) { err = "temporal blocking was removed in ABI 2 (measured slower than the single-step kernel; DESIGN.md)"; return FVDBM_ERR_UNSUPPORTED; }
@@ -917,7 +883,7 @@ struct EngineT final : Engine {
                            npdf.bytes() + nrho.bytes() + nvel.bytes() + s_cface.bytes() + s_csign.bytes() + s_fcell.bytes() +
                            s_fnode.bytes() + s_fdist.bytes() + s_fn.bytes() + s_fL.bytes() + s_inv_area.bytes() + s_rho.bytes() +
                            s_ux.bytes() + s_uy.bytes() + s_feq.bytes() + s_flux.bytes() + inbox.bytes() + outbox[0].buf.bytes() + outbox[1].buf.bytes() + halo_send.bytes() +
-                           halo_recv.bytes() + sendbuf.bytes() + recvbuf.bytes() + counter.bytes() + stepsync.bytes());
+                           halo_recv.bytes() + sendbuf.bytes() + recvbuf.bytes() + counter.bytes());
             break;
         case FVDBM_INFO_VARIANT: *v = variant; break;
         case FVDBM_INFO_NPAD: *v = plan.Npad; break;

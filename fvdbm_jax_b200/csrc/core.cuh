@@ -31,10 +31,8 @@
 #endif
 #if defined(__CUDA_ARCH__)
 #define FVDBM_LDG(p) __ldg(p)
-#define FVDBM_LDCG(p) __ldcg(p)
 #else
 #define FVDBM_LDG(p) (*(p))
-#define FVDBM_LDCG(p) (*(p))
 #endif
 
 namespace fvdbm {
@@ -287,28 +285,19 @@ struct GhostTables {
 
 // populations on the far side of one side of ONE cell: the neighbour's (gathered by `gather(pos, fn)`)
 // or the ghost cell's (src/containers.py:285-287: mean of the two node PDFs, extrapolated through it)
-// ghost cell behind boundary side `cd` (< 0).  L2_ONLY: the node populations are read with ld.global.cg -- for the
-// single-kernel step (kernels.cuh: k_step_rec), where other CTAs of the SAME grid write them (no L1 / non-coherent path)
-template <typename S, int Q, bool L2_ONLY = false>
-FVDBM_HD void ghost_populations(const GhostTables<S>& G, int32_t cd, const S* f, S* fn) {
-    const int32_t b = (-(cd + 1)) >> 2;
-    const S ratio = FVDBM_LDG(G.bf_ratio + b);
-    const int32_t na = FVDBM_LDG(G.bf_na + b), nb = FVDBM_LDG(G.bf_nb + b);
-#pragma unroll
-    for (int q = 1; q < Q; ++q) {
-        const S pa = L2_ONLY ? FVDBM_LDCG(G.npdf + q * G.NTpad + na) : FVDBM_LDG(G.npdf + q * G.NTpad + na);
-        const S pb = L2_ONLY ? FVDBM_LDCG(G.npdf + q * G.NTpad + nb) : FVDBM_LDG(G.npdf + q * G.NTpad + nb);
-        const S g = v_mul(v_add(pa, pb), S(0.5));
-        fn[q] = v_fma(v_sub(g, f[q]), ratio, g);
-    }
-}
-
 template <typename S, int Q, typename Gather>
 FVDBM_HD void far_populations(const GhostTables<S>& G, int32_t cd, const S* f, Gather&& gather, S* fn) {
     if (cd >= 0) {
         gather((int64_t)(cd >> 2), fn);
     } else {
-        ghost_populations<S, Q>(G, cd, f, fn);
+        const int32_t b = (-(cd + 1)) >> 2;
+        const S ratio = FVDBM_LDG(G.bf_ratio + b);
+        const int32_t na = FVDBM_LDG(G.bf_na + b), nb = FVDBM_LDG(G.bf_nb + b);
+#pragma unroll
+        for (int q = 1; q < Q; ++q) {
+            const S g = v_mul(v_add(FVDBM_LDG(G.npdf + q * G.NTpad + na), FVDBM_LDG(G.npdf + q * G.NTpad + nb)), S(0.5));
+            fn[q] = v_fma(v_sub(g, f[q]), ratio, g);
+        }
     }
     fn[0] = S(0);
 }

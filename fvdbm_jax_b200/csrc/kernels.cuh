@@ -287,40 +287,18 @@ __device__ __forceinline__ void st_record256(float* p, const float2* o) {
 #ifndef FVDBM_REC_MINCTAS
 #define FVDBM_REC_MINCTAS 5           // A/B on B200: 256x5 (48 regs, no spills) 0.2058 ms sustained vs 256x3/4 (56 regs) 0.2093, 128x8 0.2072
 #endif
-// Counters of the single-kernel step (k_step_rec below): node CTAs arrive on `done`, every CTA on `finished`.
-struct StepSync {
-    unsigned* done;        // node CTAs that have published their nodes in this launch
-    unsigned* finished;    // CTAs of this launch that have exited (the last one resets both counters)
-    unsigned* error;       // set if a wait ever timed out (never in a correct run; keeps a bug from hanging the GPU)
-};
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// One cell per thread of CTA-index `block_index` (of `nblk`) over the record layout.  FUSED = false: the body of k_fused_rec
-// (boundary nodes were updated by the preceding k_nodes launch).  FUSED = true: the cell part of k_step_rec -- the
-// predecessor kernel wrote pdf_in, so only the static operands are loaded ahead of the PDL wait, and a CTA that owns a
-// ghost side first waits until the `node_blocks` node CTAs of the SAME grid have published the node populations.
-template <int K, int SCHEME, bool FUSED>
-__device__ __forceinline__ void rec_cell_update(const FusedArgs<float>& a, const int64_t block_index, const int64_t nblk,
-                                                const int node_blocks, const StepSync& sync) {
+template <int K, int SCHEME>
+__global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_REC_MINCTAS) k_fused_rec(const FusedArgs<float> a) {
     constexpr int Q = 9, NC = SCHEME == 0 ? 2 : 4;
     const int64_t Npad = a.Npad;
-    const int64_t blk = a.reverse ? (nblk - 1 - block_index) : block_index;
-    int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
+    const int64_t nblk = gridDim.x;
+    const int64_t blk = a.reverse ? (nblk - 1 - blockIdx.x) : blockIdx.x;
+    const int64_t c = a.cell_begin + blk * blockDim.x + threadIdx.x;
     const float* rest_in = a.pdf_in + (size_t)Npad * (Q - 1);
     if (a.prefetch_dist > 0 && threadIdx.x == 0)
         prefetch_cells_rec_l2<float, Q, K, NC>(a, a.cell_begin + (blk + (a.reverse ? -a.prefetch_dist : a.prefetch_dist)) * (int64_t)blockDim.x,
                                                (int)blockDim.x);
-    bool inrange = true;
-    if (FUSED) {                                   // every thread must reach the CTA barriers below
-        inrange = c < a.cell_end;
-        if (!inrange) c = a.cell_begin;
-    } else if (c >= a.cell_end) {
-        return;
-    }
+    if (c >= a.cell_end) return;
     const size_t tile = (size_t)(c >> 5);
     const int lane = (int)(c & 31);
     const int32_t* gc = a.ccode + tile * (K * kTW) + lane;
@@ -332,32 +310,12 @@ __device__ __forceinline__ void rec_cell_update(const FusedArgs<float>& a, const
 #pragma unroll
     for (int i = 0; i < K * NC; ++i) coef[i] = __ldg(gco + i * kTW);
     float2 f[4];                                                                          // (q1,q2) (q3,q4) (q5,q6) (q7,q8)
-    float f0;
-    const bool live = inrange && code[0] != kHole;
+    ld_record256(a.pdf_in + (size_t)c * (Q - 1), f);
+    const float f0 = __ldg(rest_in + c);
+    const bool live = code[0] != kHole;
     if (!live) code[0] = 0;                        // neutral: interior side towards position 0
-    if (!FUSED) {                                  // pdf_in was complete before the predecessor (k_nodes) started
-        ld_record256(a.pdf_in + (size_t)c * (Q - 1), f);
-        f0 = __ldg(rest_in + c);
-    }
     pdl_wait();
     pdl_trigger();
-    if (FUSED) {
-        ld_record256(a.pdf_in + (size_t)c * (Q - 1), f);
-        f0 = __ldg(rest_in + c);
-        bool ghost = false;
-#pragma unroll
-        for (int k = 0; k < K; ++k) ghost |= code[k] < 0;
-        if (__syncthreads_or(live && ghost)) {     // border CTA: the node CTAs (lowest block indices, dispatched first) publish
-            if (threadIdx.x == 0) {                // the node populations of this iteration, then count themselves on `done`
-                unsigned spins = 0;
-                while (ld_acquire_gpu(sync.done) < (unsigned)node_blocks) {
-                    __nanosleep(32);
-                    if (++spins > (1u << 22)) { atomicExch(sync.error, 1u); break; }
-                }
-            }
-            __syncthreads();
-        }
-    }
     float2 fl[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -368,7 +326,7 @@ __device__ __forceinline__ void rec_cell_update(const FusedArgs<float>& a, const
         } else {                                    // ghost side (border cells only): scalar path of core.cuh
             const float fo[Q] = {f0, f[0].x, f[0].y, f[1].x, f[1].y, f[2].x, f[2].y, f[3].x, f[3].y};
             float g[Q];
-            ghost_populations<float, Q, FUSED>(a.G, cd, fo, g);
+            far_populations<float, Q>(a.G, cd, fo, [](int64_t, float*) {}, g);
             fn[0] = f2(g[1], g[2]); fn[1] = f2(g[3], g[4]); fn[2] = f2(g[5], g[6]); fn[3] = f2(g[7], g[8]);
         }
         const bool slot1 = code_slot(cd) != 0, neg = code_neg(cd) != 0;
@@ -428,11 +386,6 @@ __device__ __forceinline__ void rec_cell_update(const FusedArgs<float>& a, const
         st_record256(a.pdf_out + (size_t)c * (Q - 1), out);
         a.pdf_out[(size_t)Npad * (Q - 1) + c] = out0;
     }
-}
-
-template <int K, int SCHEME>
-__global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_REC_MINCTAS) k_fused_rec(const FusedArgs<float> a) {
-    rec_cell_update<K, SCHEME, false>(a, blockIdx.x, gridDim.x, 0, StepSync{nullptr, nullptr, nullptr});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -593,7 +546,8 @@ __device__ __forceinline__ real group_sum(real v) {          // xor butterfly in
 // (A full warp per node left 24+ lanes idle and spent ~1500 warp-instructions per node: 26 us for the 19.5k
 // boundary nodes of the porous config; profiles/r2_launches_porous.csv.)
 template <typename real, int Q>
-__device__ __forceinline__ void node_group_update(const NodeArgs<real>& a, const int gtid) {
+__global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
+    const int gtid = (int)(blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
     const int sub = threadIdx.x & (kNodeLanes - 1);
     const bool valid = gtid / kNodeLanes < a.NA;
     const int node = valid ? gtid / kNodeLanes : 0;          // idle groups shadow node 0 so that shuffles stay convergent
@@ -630,46 +584,6 @@ __device__ __forceinline__ void node_group_update(const NodeArgs<real>& a, const
         if (type == 2) { a.nvel[node] = ux_n; a.nvel[a.NTpad + node] = uy_n; }
 #pragma unroll
         for (int q = 0; q < Q; ++q) a.npdf[q * a.NTpad + node] = pdf_n[q];
-    }
-}
-
-template <typename real, int Q>
-__global__ void __launch_bounds__(256) k_nodes(const NodeArgs<real> a) {
-    node_group_update<real, Q>(a, (int)(blockIdx.x * (int64_t)blockDim.x + threadIdx.x));
-}
-
-// ------------------------------------------------------------------------------------------------
-// The whole iteration in ONE launch (fp32 D2Q9 records, single handle, latency-bound meshes): CTAs [0, node_blocks) are
-// k_nodes, the rest is k_fused_rec.  Interior cells never look at boundary nodes, so only the CTAs that own a ghost side
-// (the border group: the LAST cell CTAs, dispatched last) wait -- on a counter the node CTAs (the FIRST CTAs, dispatched
-// first, so they are resident before anything can wait for them) bump after publishing their nodes.  Compared with the
-// [k_nodes -> cells] chain this removes one dependent launch per iteration and hides the node update behind the interior
-// cells.  Chain rule as before: every CTA passes griddepcontrol.wait before it touches populations, node arrays or the
-// counters, and triggers its dependents right after, so at most two consecutive launches overlap and the predecessor
-// (which wrote pdf_in and reset the counters) is complete.  Same device functions as the two-kernel path -> same bits.
-// ------------------------------------------------------------------------------------------------
-#ifndef FVDBM_STEP_MINCTAS
-#define FVDBM_STEP_MINCTAS 4          // the node path needs 58 registers; occupancy is irrelevant on the meshes this is used for
-#endif
-template <int K, int SCHEME>
-__global__ void __launch_bounds__(FVDBM_REC_THREADS, FVDBM_STEP_MINCTAS)
-k_step_rec(const FusedArgs<float> a, const NodeArgs<float> na, const int node_blocks, const StepSync sync) {
-    if ((int)blockIdx.x < node_blocks) {
-        node_group_update<float, 9>(na, (int)(blockIdx.x * (int64_t)blockDim.x + threadIdx.x));
-        __threadfence();                               // each writer's node values are visible device-wide ...
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); atomicAdd(sync.done, 1u); }   // ... before the CTA counts itself
-    } else {
-        rec_cell_update<K, SCHEME, true>(a, (int64_t)blockIdx.x - node_blocks, (int64_t)gridDim.x - node_blocks, node_blocks, sync);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {                            // last CTA out: nobody waits any more -> rearm for the next launch
-        __threadfence();
-        if (atomicAdd(sync.finished, 1u) == gridDim.x - 1) {
-            atomicExch(sync.done, 0u);
-            atomicExch(sync.finished, 0u);
-            __threadfence();
-        }
     }
 }
 

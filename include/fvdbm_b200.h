@@ -70,7 +70,7 @@ extern "C" {
 /* All variants execute the same canonical operation sequence: results are bit-identical.
  * Debug / A-B environment overrides read once at fvdbm_create (each mirrors an fvdbm_option):
  *   FVDBM_VARIANT, FVDBM_TILE_CELLS, FVDBM_STAGES, FVDBM_GRAPH_STEPS, FVDBM_CTAS_PER_SM,
- *   FVDBM_REVERSE_SWEEP, FVDBM_PDL, FVDBM_FUSE_NODES, FVDBM_PREFETCH_DIST, FVDBM_OVERLAP (0: no side stream for the interior cells),
+ *   FVDBM_REVERSE_SWEEP, FVDBM_PDL, FVDBM_PREFETCH_DIST, FVDBM_OVERLAP (0: no side stream for the interior cells),
  *   FVDBM_PLAN_THREADS (host planner threads), FVDBM_NCCL_LIB (path of libnccl to dlopen). */
 
 /* fields for fvdbm_get / fvdbm_set (reference attribute in brackets) */
@@ -112,10 +112,8 @@ enum fvdbm_option {
     FVDBM_OPT_PREFETCH_DIST = 7,  /* >0: each CTA bulk-prefetches into L2 the streaming operands of the CTA this
                                      many blocks ahead (direct / pair kernels); 0 = off                      */
     FVDBM_OPT_PDL = 8,            /* 1: single-stream [nodes -> cells] chain with programmatic dependent launches
-                                     (default below 1.5M cells, where the step is launch-latency bound); 0: two-stream
+                                     (default below 1M cells, where the step is launch-latency bound); 0: two-stream
                                      overlap schedule (default above)                                          */
-    FVDBM_OPT_FUSE_NODES = 9,     /* 1 (default): inside the PDL chain, fp32 D2Q9 over records runs an iteration as ONE launch
-                                     (boundary-node CTAs + cell CTAs, k_step_rec); 0: [k_nodes -> cells], two launches      */
     FVDBM_OPT_TEMPORAL = 6        /* removed in ABI 2 (two-iterations-per-pass temporal blocking halved the DRAM
                                      traffic but measured slower); 0 accepted, 1 -> ERR_UNSUPPORTED */
 };

@@ -163,15 +163,10 @@ def test_fused_variants_bitwise_identical():
     configs += [dict(variant=_lib.VARIANT_DIRECT, pdl=0), dict(variant=_lib.VARIANT_DIRECT, pdl=0, graph=8),
                 dict(variant=_lib.VARIANT_DIRECT, pdl=1, graph=8), dict(variant=_lib.VARIANT_PAIR, pdl=1, graph=0),
                 dict(variant=_lib.VARIANT_TMA, tile=128, stages=2, pdl=1, graph=4)]
-    # record kernel inside the PDL chain: one launch per iteration (k_step_rec: node CTAs + cell CTAs) vs [k_nodes -> cells]
-    configs += [dict(variant=_lib.VARIANT_REC, pdl=1, fuse=0, graph=0), dict(variant=_lib.VARIANT_REC, pdl=1, fuse=1, graph=0),
-                dict(variant=_lib.VARIANT_REC, pdl=1, fuse=1, graph=8, reverse=1), dict(variant=_lib.VARIANT_REC, pdl=0, fuse=1, graph=0)]
     for cfg in configs:
         env = fb.Environment(cells, faces, nodes, dtype=np.float32, reorder=cfg.get("reorder", "none"))
         env.init()
         env.set_option(_lib.OPT_VARIANT, cfg["variant"])
-        if "fuse" in cfg:
-            env.set_option(_lib.OPT_FUSE_NODES, cfg["fuse"])
         if "tile" in cfg:
             env.set_option(_lib.OPT_TILE_CELLS, cfg["tile"]).set_option(_lib.OPT_STAGES, cfg["stages"])
         env.set_option(_lib.OPT_REVERSE_SWEEP, cfg.get("reverse", 0)).set_option(_lib.OPT_GRAPH_STEPS, cfg.get("graph", 0))
@@ -185,50 +180,6 @@ def test_fused_variants_bitwise_identical():
         else:
             for a, b in zip(ref, got):
                 np.testing.assert_array_equal(a, b, err_msg=str(cfg))
-        env.close()
-
-
-@pytest.mark.parametrize("problem", ["cylinder_rho_outlet", "quads_d2q9", "tri_upwind", "tiny"])
-def test_single_launch_step_equals_the_two_kernel_chain(problem):
-    """k_step_rec (boundary-node CTAs + cell CTAs in one launch, border CTAs wait on a device counter) against the
-    [k_nodes -> k_fused_rec] chain: bit-identical cells AND nodes, with and without graph batching, over many iterations
-    (so that the counters are re-armed hundreds of times), one launch per iteration."""
-    if problem == "cylinder_rho_outlet":
-        raw = meshgen.cylinder_channel(scale=3)
-        m = fb.Mesher(); m.import_meshpy(raw); m.calc_mesh_properties()
-        dyn = fb.D2Q9(tau=0.65, delta_t=0.1)
-        cells, faces, nodes = m.to_env(dyn, flux_method="lax_wendroff")
-        for mk, vel in ((4, (0.1, 0.0)), (3, (0.0, 0.0)), (1, (0.0, 0.0)), (5, (0.0, 0.0))):
-            nodes = m.set_vel_node(nodes, mk, np.array(vel))
-        nodes = m.set_rho_node(nodes, 2, 0.95)
-    elif problem == "quads_d2q9":
-        cells, faces, nodes = meshgen.quad_cavity(40, 30, fb.D2Q9(tau=0.8, delta_t=0.1), 0.1)
-    else:
-        nx, ny = (2, 1) if problem == "tiny" else (50, 40)
-        m = fb.Mesher(); m.import_meshpy(meshgen.triangulated_square(nx, ny, seed=9)); m.calc_mesh_properties()
-        dyn = fb.D2Q9(tau=0.8, delta_t=0.1)
-        cells, faces, nodes = m.to_env(dyn, flux_method="upwind" if problem == "tri_upwind" else "lax_wendroff")
-        for mk, vel in ((1, (0.0, 0.0)), (2, (0.0, 0.0)), (4, (0.0, 0.0)), (3, (0.1, 0.0))):
-            nodes = m.set_vel_node(nodes, mk, np.array(vel))
-    ref = None
-    for fuse, graph in ((0, 0), (1, 0), (1, 50), (0, 50)):
-        env = fb.Environment(cells, faces, nodes, dtype=np.float32)
-        env.init()
-        env.set_option(_lib.OPT_VARIANT, _lib.VARIANT_REC).set_option(_lib.OPT_PDL, 1)
-        env.set_option(_lib.OPT_FUSE_NODES, fuse).set_option(_lib.OPT_GRAPH_STEPS, graph)
-        l0 = env.info(_lib.INFO_LAUNCHES)
-        env = env.step(333)
-        env.sync()
-        per_step = (env.info(_lib.INFO_LAUNCHES) - l0) / 333
-        assert per_step == (1 if fuse else 2), (fuse, graph, per_step)
-        got = {k: np.array(getattr(getattr(env, k.split(".")[0]), k.split(".")[1])) for k in
-               ("cells.pdf", "cells.rho", "cells.vel", "nodes.pdf", "nodes.rho", "nodes.vel")}
-        assert np.isfinite(got["cells.pdf"]).all()
-        if ref is None:
-            ref = got
-        else:
-            for k in ref:
-                np.testing.assert_array_equal(ref[k], got[k], err_msg=f"{problem} {k} fuse={fuse} graph={graph}")
         env.close()
 
 

@@ -18,10 +18,4 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 3
 echo "ncu launches rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))s"
 timeout 150 python tools/configs_bench.py > gpurun_out/small_configs.jsonl 2> gpurun_out/small_configs.err
 echo "small configs rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))s"; cut -c1-220 gpurun_out/small_configs.jsonl
-FVDBM_FUSE_NODES=0 timeout 100 python tools/configs_bench.py --graphs 50 > gpurun_out/small_configs_two_launches.jsonl 2>> gpurun_out/small_configs.err
-cut -c1-220 gpurun_out/small_configs_two_launches.jsonl
-timeout 100 python tools/variant_crossover.py --nx 224,354,500,708,866 --variants 4 > gpurun_out/crossover_one_launch.jsonl 2>> gpurun_out/small_configs.err
-FVDBM_FUSE_NODES=0 timeout 100 python tools/variant_crossover.py --nx 224,354,500,708,866 --variants 4 > gpurun_out/crossover_two_launches.jsonl 2>> gpurun_out/small_configs.err
-cat gpurun_out/crossover_one_launch.jsonl gpurun_out/crossover_two_launches.jsonl
-echo "A/B rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))s"
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
