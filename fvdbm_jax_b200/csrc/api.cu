@@ -145,9 +145,9 @@ struct EngineT final : Engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap = 1;
     int mode = FVDBM_MODE_FUSED;
-    int variant = FVDBM_VARIANT_DIRECT;   // fp32: PAIR (two cells per thread, packed math); fp64: DIRECT; TMA is opt-in
+    int variant = FVDBM_VARIANT_DIRECT;   // replaced by default_variant() at init: fp32 D2Q9 REC, fp64 DIRECT; TMA is opt-in
     int tile_cells = 256, stages = 3, graph_steps = 0, ctas_per_sm = 0, reverse_sweep = 0;
-    int pdl = 0;                         // programmatic dependent launch chain (default: on below 1M cells)
+    int pdl = 0;                         // programmatic dependent launch chain (default: on below 1.5M cells)
     int lay = 0;                         // population layout of pdf[0..1] (core.cuh: 0 tiled AoSoA, 1 records); follows the variant
     int prefetch_dist = 296;             // CTAs of L2 look-ahead (0.4 of a resident wave); measured on B200: burst 0.231 -> 0.194 ms per
                                          // 10M-cell iteration, sustained +2-3 % (profiles/r2_ab_pair_kernel.jsonl)

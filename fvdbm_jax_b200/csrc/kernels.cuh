@@ -1,9 +1,9 @@
 // kernels.cuh -- sm_100a kernels of the FVDBM step (see DESIGN.md for the roofline of each).
 //
-//   k_nodes         S3  boundary nodes: one warp per active node, shuffle reduction over its ring
-//   k_fused_pair    S1+S2+S4+S5 cell-centric, TWO cells per thread: packed fp32 math (FFMA2/FADD2/FMUL2),
-//                   64-bit coalesced streaming loads/stores; fp32 default
-//   k_fused_direct  same arithmetic, one cell per thread (fp64 default; fp32 A/B partner)
+//   k_nodes         S3  boundary nodes: 8 lanes per active node, shuffle butterfly over its ring
+//   k_fused_rec     S1+S2+S4+S5 cell-centric over the RECORD layout, one 256-bit access per record, FFMA2 over population
+//                   pairs; fp32 D2Q9 default.   k_fused_pair: TWO cells per thread over AoSoA (fp32 D2Q13 >= 4M cells)
+//   k_fused_direct  same arithmetic, one cell per thread, either layout (fp64 default; fp32 A/B partner)
 //   k_fused_tma     same arithmetic; persistent CTAs, cp.async.bulk (TMA) + mbarrier ring of tiles
 //   k_s_*           staged (reference-shaped) kernels S1/S2, S4, S5 -- general meshes + observables
 //   k_export_* / k_import_* / k_pack / k_unpack   layout conversion at the API boundary

@@ -112,7 +112,7 @@ enum fvdbm_option {
     FVDBM_OPT_PREFETCH_DIST = 7,  /* >0: each CTA bulk-prefetches into L2 the streaming operands of the CTA this
                                      many blocks ahead (direct / pair kernels); 0 = off                      */
     FVDBM_OPT_PDL = 8,            /* 1: single-stream [nodes -> cells] chain with programmatic dependent launches
-                                     (default below 1M cells, where the step is launch-latency bound); 0: two-stream
+                                     (default below 1.5M cells, where the step is launch-latency bound); 0: two-stream
                                      overlap schedule (default above)                                          */
     FVDBM_OPT_TEMPORAL = 6        /* removed in ABI 2 (two-iterations-per-pass temporal blocking halved the DRAM
                                      traffic but measured slower); 0 accepted, 1 -> ERR_UNSUPPORTED */
