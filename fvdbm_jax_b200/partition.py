@@ -206,30 +206,35 @@ def extract_local(g: GlobalMesh, part: np.ndarray, rank: int, reorder: bool = Tr
     is_owned = np.zeros(N, dtype=bool)
     is_owned[owned] = True
 
-    faces_l = np.unique(g.face_indices[owned].reshape(-1))
+    def unique_ids(ids, size):
+        """Sorted unique non-negative ids < size: a mark-and-scan (O(n + size)) instead of np.unique's sort."""
+        mark = np.zeros(size, dtype=bool)
+        mark[ids[ids >= 0]] = True
+        return np.nonzero(mark)[0]
+
+    F_all, P_all = g.stencil.shape[0], g.node_type.shape[0]
+    faces_l = unique_ids(g.face_indices[owned].reshape(-1), F_all)
     st = g.stencil[faces_l]
     nbr = st.reshape(-1)
     nbr = nbr[nbr >= 0]
     halo_a = nbr[~is_owned[nbr]]
     # (B) rings of active nodes on boundary faces of owned cells
     bfaces = faces_l[(st[:, 0] < 0) | (st[:, 1] < 0)]
-    bnodes = np.unique(g.nodes_index[bfaces].reshape(-1))
-    bnodes = bnodes[bnodes >= 0]
+    bnodes = unique_ids(g.nodes_index[bfaces].reshape(-1), P_all)
     active = bnodes[g.node_type[bnodes, 0] != 0]
     ring = g.ring[active]
     ring_ok = (ring >= 0) & (g.ring_dists[active] > 0)
     rc = ring[ring_ok]
     halo_b = rc[~is_owned[rc]]
-    halo = np.unique(np.concatenate([halo_a, halo_b]))
+    halo = unique_ids(np.concatenate([halo_a, halo_b]), N)
     hkey = np.lexsort((gid_of[halo], part[halo]))
     halo = halo[hkey]
     cells_l = np.concatenate([owned, halo])
     lid = -np.ones(N, dtype=np.int64)
     lid[cells_l] = np.arange(cells_l.shape[0])
 
-    nodes_l = np.unique(g.nodes_index[faces_l].reshape(-1))
-    nodes_l = nodes_l[nodes_l >= 0]
-    P = g.node_type.shape[0]
+    nodes_l = unique_ids(g.nodes_index[faces_l].reshape(-1), P_all)
+    P = P_all
     nlid = -np.ones(P, dtype=np.int64)
     nlid[nodes_l] = np.arange(nodes_l.shape[0])
     F = g.stencil.shape[0]
