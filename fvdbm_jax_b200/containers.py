@@ -102,6 +102,32 @@ class Faces(Container):
         self.stencil_dists = np.asarray(self.stencil_dists)
 
 
+class CCStencilFaces(Faces):
+    """reference src/faces.py:10-76: ``n`` is the cell-centre stencil direction, ``alpha`` its angle to the face normal;
+    the flux is the plain scheme's times cos(alpha) (Environment folds it into the face length)."""
+
+    def __init__(self, size, dynamics: Dynamics, flux_scheme: str = "upwind"):
+        super().__init__(size, dynamics, flux_scheme=flux_scheme)
+        self.alpha = np.zeros((size, 1), dtype=np.float64)
+
+    def init(self):
+        super().init()
+        self.alpha = np.asarray(self.alpha)
+
+
+class CCStencilKsiFaces(Faces):
+    """reference src/faces.py:78-141 (``cc_alt_upwind``): divides by KSI.n_PQ, which is 0 for axis-aligned stencils, so the
+    reference itself produces NaN; ``Environment`` refuses it with a ValueError.  Present for import compatibility."""
+
+    def __init__(self, size, dynamics: Dynamics, flux_scheme: str = "upwind"):
+        super().__init__(size, dynamics, flux_scheme=flux_scheme)
+        self.npq = np.zeros((size, dynamics.DIM), dtype=np.float64)
+
+    def init(self):
+        super().init()
+        self.npq = np.asarray(self.npq)
+
+
 class Nodes(Container):
     """reference containers.py:294-408"""
 

@@ -20,7 +20,7 @@ from __future__ import annotations
 import pickle
 import numpy as np
 
-from .containers import Cells, Faces, Nodes
+from .containers import CCStencilFaces, Cells, Faces, Nodes
 from .environment import Environment
 
 __all__ = ["Mesher"]
@@ -345,9 +345,11 @@ class Mesher:
         cells.face_normals = np.asarray(self.cell_face_normal_signs, dtype=np.int32)
         cells.centers = np.asarray(self.cell_centers, dtype=np.float64)   # extension: locality renumbering
 
-        faces = Faces(self.faces.shape[0], dynamics, flux_scheme=flux_method[3:] if cc else flux_method)
         if cc:
+            faces = CCStencilFaces(self.faces.shape[0], dynamics, flux_scheme=flux_method[3:])
             faces.alpha = np.asarray(self.face_stencil_angles, dtype=np.float64)[..., np.newaxis]
+        else:
+            faces = Faces(self.faces.shape[0], dynamics, flux_scheme=flux_method)
         faces.n = np.asarray(self.stencil_norms if cc else self.face_normals, dtype=np.float64)
         unit = dim_multiplier == 1               # x * 1 is the identity bit for bit: skip the passes over 10^7-row arrays
         faces.L = np.asarray(self.face_lengths, dtype=np.float64)[..., np.newaxis]

@@ -451,3 +451,54 @@ def test_cc_alt_variant_is_rejected_like_it_fails_in_the_reference():
     faces.npq = np.zeros_like(faces.n)
     with pytest.raises(ValueError, match="CCStencilKsiFaces"):
         fb.Environment(cells, faces, nodes)._describe()
+
+
+COMPAT_NOTEBOOK = r"""
+import sys
+sys.path.append('..')                                   # the notebooks' first line: harmless here
+import fvdbm_jax_b200.compat; fvdbm_jax_b200.compat.install()   # <- the one added line
+from src.dynamics import *
+from src.environment import *
+from src.mesher import *
+from src.containers import *
+from src.cells import *
+from src.faces import *
+from src.nodes import *
+from utils.test_utils import *
+import numpy as np
+import fvdbm_jax_b200 as fb
+from fvdbm_jax_b200 import meshgen
+assert Environment is fb.Environment and Mesher is fb.Mesher and Cells is fb.Cells and Faces is fb.Faces and Nodes is fb.Nodes
+assert D2Q9 is fb.D2Q9 and D2Q13 is fb.D2Q13 and CustomArray is fb.CustomArray and CCStencilFaces is fb.CCStencilFaces
+# tests/flow_over_cyl.ipynb c10-c16 with the synthetic triangulation standing in for meshpy.triangle
+mesher = Mesher()
+mesher.import_meshpy(meshgen.cylinder_channel(scale=1))
+mesher.calc_mesh_properties()
+dynamics = D2Q9(tau=0.65, delta_t=0.1)
+cells, faces, nodes = mesher.to_env(dynamics, flux_method="lax_wendroff")
+nodes = mesher.set_vel_node(nodes, marker=4, velocity=np.array([0.1, 0.0]))
+nodes = mesher.set_rho_node(nodes, marker=2, rho=0.95)
+env = Environment(cells, faces, nodes)
+env.init()
+assert env.cells.pdf.shape == (2392, 9) and "Environment(cells=" in repr(env)
+# tests/ldcFVDBM.ipynb c4-c9: Environment.create + CustomArray.add_items
+Environment.dynamics = D2Q13(tau=0.8, delta_t=0.1)
+env2 = Environment.create(4, 12, 9)
+env2.cells.face_indices.add_items(0, np.asarray([0, 1, 2, 3]))
+env2.init()
+assert np.asarray(env2.cells.face_indices)[0].tolist() == [0, 1, 2, 3]
+cc = mesher.to_env(dynamics, flux_method="cc_upwind")[1]
+assert isinstance(cc, CCStencilFaces) and cc.alpha.shape == (mesher.faces.shape[0], 1)
+assert abs(extrap_pdf(2.0, 1.0, 0.5, 1.0) - 2.5) < 1e-15 and Key(0)() is not None
+print("compat ok")
+"""
+
+
+def test_reference_module_names_resolve_to_this_framework():
+    """fvdbm_jax_b200.compat: the notebooks' own ``from src.environment import *`` ... lines, unedited, bind this
+    framework's classes after one added line (run in a subprocess: the oracle tests import the REAL reference under
+    the same module names)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", COMPAT_NOTEBOOK], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0 and "compat ok" in r.stdout, r.stderr[-3000:]

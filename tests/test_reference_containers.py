@@ -80,3 +80,25 @@ def test_stencil_geometry_report_equals_the_reference_printout(capsys):
         assert num.sub("#", a) == num.sub("#", b)                   # same text
         for x, y in zip(num.findall(a), num.findall(b)):
             assert abs(float(x) - float(y)) <= 1e-9 + 2e-3 * abs(float(x)), (a, b)
+
+
+def test_utils_helpers_equal_the_reference_functions():
+    """fvdbm_jax_b200.utils against /root/reference/utils/utils.py executed under the shim."""
+    from fvdbm_jax_b200 import utils as ours
+    ref = refrun.load().utils
+    rng = np.random.default_rng(7)
+    x, w = rng.random((6, 9)), rng.random(6) + 0.1
+    d = np.array([0.5, 1.5, -1.0, 2.0, -1.0, 0.7])
+    assert np.allclose(ours.weighted_avg(x, w), np.asarray(ref.weighted_avg(x, w)), rtol=1e-15, atol=0)
+    assert np.allclose(ours.extrapolate(x, d), np.asarray(ref.extrapolate(x, d)), rtol=1e-15, atol=0)
+    assert np.allclose(ours.interp_pdf(x, np.abs(d)), np.asarray(ref.interp_pdf(x, np.abs(d))), rtol=1e-15, atol=0)
+    assert np.array_equal(ours.extrap_pdf(x[0], x[1], 0.3, 0.9), np.asarray(ref.extrap_pdf(x[0], x[1], 0.3, 0.9)))
+    p1, p2 = np.array([0.2, -1.0]), np.array([1.7, 0.4])
+    assert np.allclose(ours.calc_normal(p1, p2), ref.calc_normal(p1, p2), rtol=1e-15) and abs(ours.calc_dist(p1, p2) - ref.calc_dist(p1, p2)) < 1e-15
+    ragged = [np.array([1, 2, 3]), np.array([4]), np.array([5, 6])]
+    assert np.array_equal(ours.pad_stack(ragged), np.asarray(ref.pad_stack([refrun.load().jnp.asarray(a) for a in ragged])))
+    a, b = ours.CustomArray(3, dtype=np.int32), ref.CustomArray(3, dtype=np.int32)
+    for arr in (a, b):
+        arr.add_items(1, np.asarray([7, 8, 9]))
+        arr.add_item(0, 4)
+    assert np.array_equal(np.asarray(a), np.asarray(b))
