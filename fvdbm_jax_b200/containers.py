@@ -14,6 +14,54 @@ from .dynamics import Dynamics
 __all__ = ["CustomArray", "Container", "Cells", "Faces", "Nodes"]
 
 
+class _AtIndex:
+    """``x.at[idx]`` -> functional updates that return a changed COPY, the JAX idiom the reference notebooks use on
+    container attributes while hand-building a mesh (tests/ldcFVDBM.ipynb c6-c7:
+    ``env.nodes.type = env.nodes.type.at[i].set(1)``, ``env.faces.n = env.faces.n.at[j].set(n)``)."""
+
+    def __init__(self, arr, idx=None):
+        self._arr, self._idx = arr, idx
+
+    def __getitem__(self, idx):
+        return _AtIndex(self._arr, idx)
+
+    def _updated(self, fn):
+        out = np.array(self._arr, copy=True)
+        out[self._idx] = fn(out[self._idx])
+        return out.view(Array)
+
+    def set(self, values):
+        return self._updated(lambda _: np.asarray(values))
+
+    def add(self, values):
+        return self._updated(lambda cur: cur + np.asarray(values))
+
+    def multiply(self, values):
+        return self._updated(lambda cur: cur * np.asarray(values))
+
+    def min(self, values):
+        return self._updated(lambda cur: np.minimum(cur, np.asarray(values)))
+
+    def max(self, values):
+        return self._updated(lambda cur: np.maximum(cur, np.asarray(values)))
+
+    def get(self):
+        return np.asarray(self._arr)[self._idx]
+
+
+class Array(np.ndarray):
+    """NumPy array with JAX's ``.at[...]`` functional-update property; what the containers hold before the engine is
+    built, so that notebook code written against ``jax.Array`` attributes keeps working.  ``np.asarray`` strips it."""
+
+    @property
+    def at(self):
+        return _AtIndex(self)
+
+
+def _arr(a):
+    return np.asarray(a).view(Array)
+
+
 class CustomArray:
     """Padded ragged array used while hand-building meshes (reference utils/utils.py:176-230)."""
 
@@ -60,7 +108,7 @@ class Container:
         # a real C-contiguous array (not np.broadcast_to: copies of a broadcast view come out Fortran-ordered), filled by
         # broadcast assignment, which is faster than np.repeat at 10^7 rows
         eq = np.asarray(eq)
-        self.pdf = np.empty((size,) + eq.shape, dtype=eq.dtype)
+        self.pdf = np.empty((size,) + eq.shape, dtype=eq.dtype).view(Array)
         self.pdf[...] = eq
         self.dynamics = dynamics
 
@@ -73,9 +121,9 @@ class Cells(Container):
 
     def __init__(self, size, dynamics: Dynamics):
         super().__init__(size, dynamics)
-        self.rho = np.zeros((size, 1), dtype=np.float64)
-        self.vel = np.zeros((size, dynamics.DIM), dtype=np.float64)
-        self.pdf_eq = np.zeros((size, dynamics.NUM_QUIVERS), dtype=np.float64)
+        self.rho = _arr(np.zeros((size, 1), dtype=np.float64))
+        self.vel = _arr(np.zeros((size, dynamics.DIM), dtype=np.float64))
+        self.pdf_eq = _arr(np.zeros((size, dynamics.NUM_QUIVERS), dtype=np.float64))
         self.face_indices = CustomArray(size, dtype=np.int32, default_value=-1)
         self.face_normals = CustomArray(size, dtype=np.int32, default_value=-1)
 
@@ -92,8 +140,8 @@ class Faces(Container):
         self.nodes_index = CustomArray(size, dtype=np.int32, default_value=-1)
         self.stencil_cells_index = CustomArray(size, dtype=np.int32, default_value=-1)
         self.stencil_dists = CustomArray(size, dtype=np.float64, default_value=-1)
-        self.n = np.zeros((size, dynamics.DIM), dtype=np.float64)
-        self.L = np.zeros((size, 1), dtype=np.float64)
+        self.n = _arr(np.zeros((size, dynamics.DIM), dtype=np.float64))
+        self.L = _arr(np.zeros((size, 1), dtype=np.float64))
         self.flux_scheme = flux_scheme
 
     def init(self):
@@ -133,9 +181,9 @@ class Nodes(Container):
 
     def __init__(self, size, dynamics: Dynamics):
         super().__init__(size, dynamics)
-        self.rho = np.zeros((size, 1), dtype=np.float64)
-        self.vel = np.zeros((size, dynamics.DIM), dtype=np.float64)
-        self.type = np.zeros((size, 1), dtype=np.int32)
+        self.rho = _arr(np.zeros((size, 1), dtype=np.float64))
+        self.vel = _arr(np.zeros((size, dynamics.DIM), dtype=np.float64))
+        self.type = _arr(np.zeros((size, 1), dtype=np.int32))
         self.cells_index = CustomArray(size, dtype=np.int32, default_value=-1)
         self.cell_dists = CustomArray(size, dtype=np.float64, default_value=-1)
 

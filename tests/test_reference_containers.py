@@ -102,3 +102,51 @@ def test_utils_helpers_equal_the_reference_functions():
         arr.add_items(1, np.asarray([7, 8, 9]))
         arr.add_item(0, 4)
     assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+VERBATIM_NOTEBOOK = r"""
+ROOT, REFERENCE = %r, %r
+import sys, os, json, types
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "jaxshim"))      # test-only NumPy stand-in for `jax` (not installed here)
+for name in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules[name] = types.ModuleType(name)
+import fvdbm_jax_b200.compat as compat
+compat.install()
+nb = json.load(open(os.path.join(REFERENCE, "tests", "ldcFVDBM.ipynb")))
+cells = ["".join(c["source"]) for c in nb["cells"] if c["cell_type"] == "code"]
+src = "\n".join(cells[:9]).replace("N_x = 100", "N_x = 6")
+g = {"__name__": "__main__"}
+exec(compile(src, "ldcFVDBM.ipynb", "exec"), g)
+env = g["env"]
+import numpy as np, fvdbm_jax_b200 as fb
+from fvdbm_jax_b200 import meshgen
+assert type(env) is fb.Environment
+c, f, n = meshgen.quad_cavity(6, 6, fb.D2Q13(tau=g["Tau"], delta_t=g["dt"]), g["U_lid"])
+for mine, ref, key in ((env.cells.face_indices, c.face_indices, "face_indices"), (env.cells.face_normals, c.face_normals, "face_normals"),
+                       (env.faces.nodes_index, f.nodes_index, "nodes_index"), (env.faces.stencil_cells_index, f.stencil_cells_index, "stencil"),
+                       (env.faces.stencil_dists, f.stencil_dists, "dists"), (env.faces.n, f.n, "n"), (env.faces.L, f.L, "L"),
+                       (env.nodes.type, n.type, "type"), (env.nodes.cells_index, n.cells_index, "ring"), (env.nodes.cell_dists, n.cell_dists, "ring dists"),
+                       (env.nodes.vel, n.vel, "vel")):
+    a, b = np.asarray(mine, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert a.shape == b.shape and np.allclose(a, b, rtol=1e-7, atol=0), key
+da = env._describe()
+assert da.desc.Q == 13 and da.desc.K == 4 and da.desc.N == 36
+print("notebook ok")
+"""
+
+
+def test_ldc_notebook_cells_run_verbatim_on_this_framework():
+    """The code cells c0-c8 of the reference's tests/ldcFVDBM.ipynb (imports, parameters, Environment.create, the
+    CustomArray.add_items / ``.at[...].set`` mesh construction, env.init()) are read from the reference tree and executed
+    UNCHANGED (only N_x = 100 -> 6) after ``fvdbm_jax_b200.compat.install()``; the environment they build is this
+    framework's and describes exactly the problem meshgen.quad_cavity builds (the mesh of the GPU LDC Re=100 test).
+    ``jax`` is the oracle's NumPy shim (JAX is not installed here), matplotlib a stub."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", VERBATIM_NOTEBOOK % (root, refrun.REFERENCE)], capture_output=True, text=True,
+                       cwd=os.path.join(root, "tests"), timeout=600)
+    assert r.returncode == 0 and "notebook ok" in r.stdout, r.stderr[-3000:]
+
