@@ -150,3 +150,65 @@ def test_ldc_notebook_cells_run_verbatim_on_this_framework():
                        cwd=os.path.join(root, "tests"), timeout=600)
     assert r.returncode == 0 and "notebook ok" in r.stdout, r.stderr[-3000:]
 
+
+POST_MESH_NOTEBOOK = r"""
+import sys, os, json, types
+ROOT, REFERENCE, NOTEBOOK, FIRST, LAST, MESH = %r, %r, %r, %d, %d, %r
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "jaxshim"))      # test-only NumPy stand-in for `jax` (not installed here)
+for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.path", "matplotlib.tri", "meshpy", "meshpy.triangle",
+             "meshpy.geometry", "trimesh", "shapely", "shapely.geometry", "shapely.ops"):      # plotting / mesh generation: absent
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["meshpy"].triangle, sys.modules["meshpy"].geometry = sys.modules["meshpy.triangle"], sys.modules["meshpy.geometry"]
+sys.modules["matplotlib.path"].Path = object
+import fvdbm_jax_b200.compat as compat
+compat.install()
+nb = json.load(open(os.path.join(REFERENCE, "tests", NOTEBOOK)))
+cells = ["".join(c["source"]) for c in nb["cells"] if c["cell_type"] == "code"]
+g = {"__name__": "__main__"}
+exec(compile(cells[0], NOTEBOOK + " c0", "exec"), g)                               # the import cell, unchanged
+from fvdbm_jax_b200 import meshgen
+g["mesh"] = getattr(meshgen, MESH)(scale=1)          # stands in for the meshpy.triangle / MeshRefiner cells
+os.chdir(os.environ["NB_TMP"])
+exec(compile("\n".join(cells[FIRST:LAST + 1]), NOTEBOOK, "exec"), g)              # Mesher ... Environment(...).init(), unchanged
+import numpy as np, fvdbm_jax_b200 as fb
+env, mesher = g["env"], g["mesher"]
+assert type(env) is fb.Environment and type(mesher) is fb.Mesher
+da = env._describe()
+assert da.desc.Q == 9 and da.desc.K == 3 and da.desc.scheme == 1 and abs(da.desc.tau - 0.65) < 1e-12
+t, mk = np.asarray(env.nodes.type).ravel(), np.asarray(g["mesh"].point_markers)
+if MESH == "cylinder_channel":       # c11: inlet 4 velocity, walls 1/3 and cylinder 5 no-slip, outlet 2 density
+    assert (t[mk == 2] == 2).all() and (t[np.isin(mk, (1, 3, 4, 5))] == 1).all() and (t[mk == 0] == 0).all()
+    assert np.allclose(np.asarray(env.nodes.vel)[mk == 4], [0.1, 0.0]) and np.allclose(np.asarray(env.nodes.rho)[mk == 2], 0.95)
+else:                                # c18: obstacles 5 and sides 2/4 no-slip, density 1.05 on marker 1, 0.95 on marker 3
+    assert (t[np.isin(mk, (2, 4, 5))] == 1).all() and (t[np.isin(mk, (1, 3))] == 2).all()
+    assert np.allclose(np.asarray(env.nodes.rho)[mk == 1], 1.05) and np.allclose(np.asarray(env.nodes.rho)[mk == 3], 0.95)
+    env2, mesher2 = g["Mesher"].from_pickle("porous_temp")                    # c20 wrote it, c26 reads it back
+    assert type(env2) is fb.Environment and np.array_equal(np.asarray(env2.nodes.type), np.asarray(env.nodes.type))
+    assert np.array_equal(mesher2.cell_face_indices, mesher.cell_face_indices)
+try:
+    g["MeshRefiner"](g["mesh"], [(10, 10)])
+    raise SystemExit("MeshRefiner should refuse")
+except NotImplementedError:
+    pass
+print("notebook ok")
+"""
+
+
+@pytest.mark.parametrize("notebook,first,last,mesh", [("flow_over_cyl.ipynb", 9, 12, "cylinder_channel"),
+                                                      ("porous_flow.ipynb", 16, 20, "porous_channel")])
+def test_post_mesh_notebook_cells_run_verbatim_on_this_framework(notebook, first, last, mesh, tmp_path):
+    """The import cell and the cells between mesh generation and the time loop of the two mesh-based notebooks (Mesher,
+    verify_stencil_geometry, parameters, to_env, boundary conditions, Environment(...).init(), to_pickle) are read from the
+    reference tree and executed UNCHANGED after ``fvdbm_jax_b200.compat.install()``; only ``mesh`` comes from this
+    framework's synthetic generator instead of meshpy.triangle (absent).  They must build this framework's Environment
+    with the notebook's boundary conditions."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = POST_MESH_NOTEBOOK % (root, refrun.REFERENCE, notebook, first, last, mesh)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, NB_TMP=str(tmp_path)))
+    assert r.returncode == 0 and "notebook ok" in r.stdout, r.stderr[-3000:]
+
