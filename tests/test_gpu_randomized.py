@@ -63,9 +63,9 @@ def test_random_problem_matches_oracle(seed):
             pytest.skip("random boundary conditions drove this case unstable (rounding differences are amplified)")
         with fb.Environment(cells, faces, nodes, dtype=dtype, reorder="hilbert" if seed % 2 else "rcm") as env:
             env.init()
-            if seed % 3 == 0:                                # small meshes default to the thread-per-cell AoSoA kernel:
-                env.set_option(_lib.OPT_VARIANT, _lib.VARIANT_REC)          # force the record-layout kernels on 1 of 3 seeds,
-            elif dtype is np.float32 and seed % 3 == 1:                       # the packed pair kernel on another
+            if seed % 3 == 0:                                # the record-layout kernels explicitly (the fp32 default; fp64 and
+                env.set_option(_lib.OPT_VARIANT, _lib.VARIANT_REC)          # D2Q13 run the thread-per-cell kernel over records),
+            elif dtype is np.float32 and seed % 3 == 1:                       # the packed pair kernel on another third
                 env.set_option(_lib.OPT_VARIANT, _lib.VARIANT_PAIR)
             env = env.step(steps)
             exp = o.state()
